@@ -1,0 +1,107 @@
+/*
+ * oracle/hexo_oracle.h -- TEST INFRASTRUCTURE (oracle), not product code.
+ *
+ * Plain-C CPU restatement of the reference's Monte-Carlo hot path
+ * (MartinErhardt/HestonExotics): shishua wrapper (src/RNG.cpp), AS241/PPND16
+ * (src/as241.f90), the Andersen-QE stepper and price driver
+ * (src/HSimulation.tpp) and the Asian / European payoff policies
+ * (src/inc/AsianContract.h, src/inc/VanillaContract.h).
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * --impl reference legs may load this library.  The product path
+ * (hestonexotics_b200/csrc) never links or calls it.
+ *
+ * PARITY STATUS: the reference holds no golden vectors for the MC path
+ * (SURVEY.md finding 3).  This restatement is pinned against the reference's
+ * OWN sources compiled verbatim into oracle/_ref/libhexo_ref.so (see
+ * oracle/Makefile, tests/test_oracle_vs_ref.py) and against fixtures generated
+ * from that build (tests/golden/).  The one unpinned piece is the raw shishua
+ * byte stream versus upstream shishua (source absent, see oracle/shishua.h).
+ */
+#ifndef HEXO_ORACLE_H
+#define HEXO_ORACLE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { ORACLE_ASIAN = 0, ORACLE_EUROPEAN = 1 };
+/* inverse-normal arithmetic: as-built (REAL*4 internals, as241.f90:20-25) or
+ * as-intended double precision */
+enum { ORACLE_NORMAL_F32 = 0, ORACLE_NORMAL_F64 = 1 };
+
+/* field order = HParams, src/inc/HDistribution.h:9-24 */
+typedef struct {
+  double v_0, v_m, rho, kappa, sigma;
+} oracle_hparams;
+
+typedef struct {
+  oracle_hparams p;
+  double S;
+  int32_t payoff;                 /* ORACLE_ASIAN / ORACLE_EUROPEAN */
+  uint32_t n_chains;              /* maturities, strictly increasing */
+  const double *expiries;         /* [n_chains] time_to_expiry in years */
+  const uint32_t *strike_offsets; /* [n_chains+1] prefix sums of chain sizes */
+  const double *strikes;          /* [n_opts] chain-major */
+  uint32_t steps;                 /* the reference's `steps` argument */
+} oracle_contract;
+
+/* ---- shishua (oracle/shishua.h) ------------------------------------------ */
+/* fill `n_bytes` (multiple of 128) of the stream seeded with seed[4] */
+int oracle_shishua_fill(const uint64_t seed[4], uint8_t *out, size_t n_bytes);
+
+/* ---- uniform map, src/RNG.cpp:31 ----------------------------------------- */
+double oracle_u64_to_unit(uint64_t x);
+
+/* ---- AS241 / PPND16, src/as241.f90:15-119 -------------------------------- */
+double oracle_ppnd16_f64(double p, int *ifault);
+double oracle_ppnd16_f32(double p, int *ifault); /* as built */
+/* sums of the decimal coefficients, to compare with as241.f90:45,64,83 */
+void oracle_ppnd16_hash_sums(double out[3]);
+
+/* ---- RNG wrapper, src/RNG.cpp:8-43 + src/inc/RNG.h:39-50 ------------------ */
+typedef struct oracle_rng oracle_rng;
+oracle_rng *oracle_rng_new(size_t size, unsigned int seed, int normal_mode);
+double oracle_rng_grand(oracle_rng *r);
+double oracle_rng_urand(oracle_rng *r);
+void oracle_rng_free(oracle_rng *r);
+
+/* ---- price driver, src/HSimulation.tpp:10-51 ------------------------------
+ * Race-free restatement: emulates `nthreads` OpenMP threads one after another
+ * (thread t: seed 1<<t, n_sims/nthreads paths, :27-28) and divides by n_sims
+ * (:40).  sum / sumsq (may be NULL) receive the raw payoff sums per option. */
+int oracle_price_ref(const oracle_contract *c, unsigned int n_sims, unsigned int nthreads,
+                     size_t rand_buf_size, int normal_mode, double *prices, double *sum,
+                     double *sumsq);
+
+/* ---- same model, GPU stream convention ------------------------------------
+ * Stream s is the shishua stream seeded {seed, s, 0, 0}; its u64 outputs
+ * x_0,x_1,... are consumed two per step: x_{2n} is the variance draw of the
+ * stream's n-th step (normal if psi<1.5, else the uniform of the same word),
+ * x_{2n+1} the log-spot normal.  The job's n_paths are split over
+ * n_streams_total streams (stream s gets n_paths/n_streams_total paths, +1 if
+ * s < n_paths % n_streams_total); this call runs streams
+ * [stream_begin, stream_begin+stream_count). */
+int oracle_price_stream(const oracle_contract *c, uint64_t seed, uint64_t n_paths,
+                        uint64_t n_streams_total, uint64_t stream_begin, uint64_t stream_count,
+                        int normal_mode, double *sum, double *sumsq);
+
+/* ---- tape replay ------------------------------------------------------------
+ * tape[path][step][3] = {Z_V, U_V, Z_X}; the stepper takes Z_V or U_V according
+ * to its branch.  finals[path][chain] receives the policy's final_value (Asian
+ * average or interpolated X_T).  Returns the number of steps each path took,
+ * or -1 if tape_steps was too short. */
+int oracle_replay(const oracle_contract *c, const double *tape, uint64_t n_paths,
+                  uint32_t tape_steps, double *finals);
+
+/* number of stepper invocations a path needs until its last maturity is paid
+ * (excludes the reference's trailing extra `++`, HSimulation.tpp:35) */
+uint32_t oracle_steps_to_last_expiry(const oracle_contract *c);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
