@@ -1,0 +1,810 @@
+// hestonexotics_b200/csrc/hexo_gpu.cu
+//
+// B200 (sm_100a) Heston Monte-Carlo hot path behind the C ABI of
+// include/hexo_gpu.h.  One fused kernel replaces the reference's
+// HSimulation::price<Scheme> (src/HSimulation.tpp:10-51) together with
+// everything it calls per draw: the shishua wrapper (src/RNG.cpp), PPND16
+// (src/as241.f90), the QE stepper (HSimulation.tpp:52-86) and the payoff
+// policies (src/inc/AsianContract.h, src/inc/VanillaContract.h).
+//
+// Design:
+//  * one thread = one independent shishua stream; RNG state, variance, log-spot
+//    and the running integral stay in registers; no path data touches HBM;
+//  * a generator round (16 words) is parked in a per-thread column of shared
+//    memory so the step loop can consume two words per step without being
+//    unrolled around the generator;
+//  * when a maturity is reached the 32 final values of a warp are exchanged
+//    through shared memory and each lane owns a strided subset of the strikes,
+//    so per-option sums are accumulated without atomics and in a fixed order;
+//  * warps -> block partials (shared memory), blocks -> sums (second tiny
+//    kernel), both in fixed order: results are reproducible for a given launch
+//    geometry.
+// There is deliberately no CPU fallback in this file.
+
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "../../include/hexo_gpu.h"
+#include "qe.cuh"
+#include "shishua.cuh"
+
+namespace hexo {
+
+// ---------------------------------------------------------------------------
+// error handling
+// ---------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define HEXO_CUDA(call)                                                                    \
+  do {                                                                                     \
+    cudaError_t e_ = (call);                                                               \
+    if (e_ != cudaSuccess)                                                                 \
+      return fail(e_ == cudaErrorNoDevice || e_ == cudaErrorInsufficientDriver             \
+                      ? HEXO_ERR_NO_DEVICE                                                 \
+                      : HEXO_ERR_CUDA,                                                     \
+                  "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+// ---------------------------------------------------------------------------
+// device context (one process drives one GPU)
+// ---------------------------------------------------------------------------
+struct Context {
+  bool ready = false;
+  int device = 0;
+  int sm_count = 0;
+  size_t smem_optin = 0;
+};
+static Context g_ctx;
+
+static int ensure_context() {
+  if (g_ctx.ready) return HEXO_OK;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    return fail(HEXO_ERR_NO_DEVICE, "no CUDA device: %s",
+                e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+  int dev = 0;
+  HEXO_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  HEXO_CUDA(cudaGetDeviceProperties(&prop, dev));
+  g_ctx.device = dev;
+  g_ctx.sm_count = prop.multiProcessorCount;
+  g_ctx.smem_optin = prop.sharedMemPerBlockOptin;
+  g_ctx.ready = true;
+  return HEXO_OK;
+}
+
+// ---------------------------------------------------------------------------
+// K1: fused path kernel
+// ---------------------------------------------------------------------------
+constexpr int kMaxBlock = 256;
+constexpr int kRingWords = 16;  // one shishua round
+
+struct PathArgs {
+  double v0, theta, S, lnS;
+  uint64_t seed;
+  uint64_t stream_begin;  // first global stream id of this launch
+  uint64_t stream_count;  // streams in this launch (one per thread)
+  uint64_t base_paths;    // every stream runs base_paths paths ...
+  uint64_t rem_streams;   // ... and global streams < rem_streams one more
+  uint32_t n_seg, n_opts;
+  const SegConst* segs;
+  const double* strikes;
+  double* partials;  // [gridDim.x][2*n_opts]
+};
+
+__host__ __device__ inline size_t path_kernel_smem(int block, uint32_t n_opts) {
+  const int warps = block / 32;
+  return (size_t)kRingWords * 8 * block + (size_t)32 * 8 * warps + (size_t)warps * 2 * n_opts * 8;
+}
+
+template <int PAYOFF, int NORMAL_MODE>
+__global__ void __launch_bounds__(kMaxBlock, 2) heston_qe_paths_kernel(const PathArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nthreads = blockDim.x, nwarps = nthreads >> 5;
+  uint64_t* ring = reinterpret_cast<uint64_t*>(smem_raw);           // [16][nthreads]
+  double* fvbuf = reinterpret_cast<double*>(ring + kRingWords * nthreads) + 32 * warp;
+  double* acc_all = reinterpret_cast<double*>(ring + kRingWords * nthreads) + 32 * nwarps;
+  double* my_sum = acc_all + (size_t)warp * 2 * a.n_opts;           // lane-owned slots
+  double* my_sq = my_sum + a.n_opts;
+  for (uint32_t j = lane; j < 2 * a.n_opts; j += 32) my_sum[j] = 0.0;
+
+  const uint64_t slot = (uint64_t)blockIdx.x * nthreads + tid;
+  const uint64_t sid = a.stream_begin + slot;
+  const uint64_t my_paths =
+      slot < a.stream_count ? a.base_paths + (sid < a.rem_streams ? 1u : 0u) : 0u;
+  // path counts are non-increasing in the stream id, so lane 0 holds the warp's maximum
+  const uint64_t warp_paths = __shfl_sync(0xffffffffu, my_paths, 0);
+
+  Shishua rng;
+  uint64_t* col = ring + tid;  // my column: word j at col[j*nthreads]
+  {
+    uint64_t o[16];
+    rng.init(a.seed, sid, 0, 0, o);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) col[j * nthreads] = o[j];
+  }
+  int pos = 0;
+  __syncwarp();
+
+  for (uint64_t p = 0; p < warp_paths; ++p) {
+    const bool active = p < my_paths;
+    // HQEAnderson::operator=(initial_state), HSimulation.tpp:26,87-94
+    double V = a.v0, lnX = a.lnS, X = a.S, Xprev = a.S;
+    double integral = 0.0;  // AAsianCallNonAdaptive::accumulated_value, reset per path (:34)
+    for (uint32_t k = 0; k < a.n_seg; ++k) {
+      const SegConst g = a.segs[k];
+      if (active) {
+        const uint32_t n = g.n_steps;
+        if (PAYOFF == HEXO_PAYOFF_ASIAN && k > 0 && n > 0) {
+          // The trapezoid of the step that crossed the previous expiry is added
+          // AFTER update_earliest switched the step size (HSimulation.tpp:42-44),
+          // i.e. with this segment's h.
+          integral += g.h * 0.5 * (X + Xprev);
+        }
+        const double Xa = X;
+        double sumX = 0.0;
+        for (uint32_t i = 0; i < n; ++i) {
+          if (pos == kRingWords) {
+            uint64_t o[16];
+            rng.round(o);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) col[j * nthreads] = o[j];
+            pos = 0;
+          }
+          WordDraws<NORMAL_MODE> d;
+          d.wv = col[pos * nthreads];
+          d.wx = col[(pos + 1) * nthreads];
+          pos += 2;
+          qe_step(g, a.theta, V, lnX, d);
+          if (PAYOFF == HEXO_PAYOFF_ASIAN) {
+            Xprev = X;
+            X = exp(lnX);                    // HSimulation.tpp:81-82
+            if (i + 1 < n) sumX += X;        // all but the crossing step
+          } else if (i + 2 >= n) {           // European: X is only read at the expiry
+            Xprev = X;
+            X = exp(lnX);
+          }
+        }
+        if (PAYOFF == HEXO_PAYOFF_ASIAN && n > 0) {
+          // sum over the first n-1 steps of h/2 (X_j + X_{j-1}), AsianContract.h:25-28
+          integral += g.h * 0.5 * (Xa - Xprev + 2.0 * sumX);
+        }
+      }
+      // accumulate_final_value, AsianContract.h:29-34 / VanillaContract.h:28-31
+      const double dx = X - Xprev;
+      const double fv = PAYOFF == HEXO_PAYOFF_ASIAN ? (integral + dx * g.w) / g.expiry
+                                                    : Xprev + dx * g.w;
+      __syncwarp();
+      fvbuf[lane] = fv;
+      const unsigned amask = __ballot_sync(0xffffffffu, active);
+      __syncwarp();
+      // final_payoff for every strike of this chain (HSimulation.tpp:39-40): lane
+      // l owns strikes l, l+32, ... and walks the warp's 32 final values.
+      for (uint32_t j = lane; j < g.n_strikes; j += 32) {
+        const double K = __ldg(a.strikes + g.first_opt + j);
+        double s = 0.0, q = 0.0;
+#pragma unroll 8
+        for (int l = 0; l < 32; ++l) {
+          if ((amask >> l) & 1u) {
+            const double pf = fmax(fvbuf[l] - K, 0.0);
+            s += pf;
+            q = fma(pf, pf, q);
+          }
+        }
+        my_sum[g.first_opt + j] += s;
+        my_sq[g.first_opt + j] += q;
+      }
+    }
+  }
+
+  // warps -> block partial, fixed order
+  __syncthreads();
+  const uint32_t n2 = 2 * a.n_opts;
+  for (uint32_t j = tid; j < n2; j += nthreads) {
+    double s = 0.0;
+    for (int w = 0; w < nwarps; ++w) s += acc_all[(size_t)w * n2 + j];
+    a.partials[(size_t)blockIdx.x * n2 + j] = s;
+  }
+}
+
+// blocks -> sums, fixed order
+__global__ void reduce_partials_kernel(const double* __restrict__ partials, uint32_t n_blocks,
+                                       uint32_t n2, double* __restrict__ out) {
+  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n2) return;
+  double s = 0.0;
+  for (uint32_t b = 0; b < n_blocks; ++b) s += partials[(size_t)b * n2 + j];
+  out[j] = s;
+}
+
+// ---------------------------------------------------------------------------
+// K2: raw shishua bytes
+// ---------------------------------------------------------------------------
+__global__ void shishua_streams_kernel(uint64_t seed0, uint64_t seed1_first, uint64_t seed2,
+                                       uint64_t seed3, uint32_t n_streams, uint64_t* out,
+                                       size_t words_per_stream) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_streams) return;
+  Shishua rng;
+  uint64_t o[16];
+  rng.init(seed0, seed1_first + i, seed2, seed3, o);
+  uint64_t* dst = out + (size_t)i * words_per_stream;
+  for (size_t off = 0; off < words_per_stream; off += 16) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) dst[off + j] = o[j];
+    rng.round(o);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// K3: uniform map, inverse normal
+// ---------------------------------------------------------------------------
+__global__ void u64_to_unit_kernel(const uint64_t* in, double* out, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = u64_to_unit(in[i]);
+}
+template <int NORMAL_MODE>
+__global__ void ppnd16_kernel(const double* in, double* out, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = ppnd16<NORMAL_MODE>(in[i]);
+}
+
+// ---------------------------------------------------------------------------
+// K4: tape replay (one thread per path), same stepper and policy arithmetic
+// ---------------------------------------------------------------------------
+template <int PAYOFF>
+__global__ void qe_replay_kernel(double v0, double theta, double S, double lnS, uint32_t n_seg,
+                                 const SegConst* segs, const double* tape, uint64_t n_paths,
+                                 uint32_t tape_steps, double* finals) {
+  const uint64_t path = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (path >= n_paths) return;
+  const double* t = tape + (size_t)path * tape_steps * 3;
+  double V = v0, lnX = lnS, X = S, Xprev = S, integral = 0.0;
+  uint32_t step = 0;
+  for (uint32_t k = 0; k < n_seg; ++k) {
+    const SegConst g = segs[k];
+    const uint32_t n = g.n_steps;
+    if (PAYOFF == HEXO_PAYOFF_ASIAN && k > 0 && n > 0) integral += g.h * 0.5 * (X + Xprev);
+    const double Xa = X;
+    double sumX = 0.0;
+    for (uint32_t i = 0; i < n; ++i, ++step) {
+      TapeDraws d = {t[3 * step], t[3 * step + 1], t[3 * step + 2]};
+      qe_step(g, theta, V, lnX, d);
+      if (PAYOFF == HEXO_PAYOFF_ASIAN) {
+        Xprev = X;
+        X = exp(lnX);
+        if (i + 1 < n) sumX += X;
+      } else if (i + 2 >= n) {
+        Xprev = X;
+        X = exp(lnX);
+      }
+    }
+    if (PAYOFF == HEXO_PAYOFF_ASIAN && n > 0) integral += g.h * 0.5 * (Xa - Xprev + 2.0 * sumX);
+    const double dx = X - Xprev;
+    finals[path * n_seg + k] =
+        PAYOFF == HEXO_PAYOFF_ASIAN ? (integral + dx * g.w) / g.expiry : Xprev + dx * g.w;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// FP64 pipe peak: 8 independent DFMA chains per thread, registers only
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, int iters, double a, double b) {
+  double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5,
+         x6 = x0 + 6, x7 = x0 + 7;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+      x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+    }
+  }
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+}
+
+// ---------------------------------------------------------------------------
+// host: schedule and segment constants
+// ---------------------------------------------------------------------------
+
+// Replays the reference's time bookkeeping in plain double arithmetic:
+// cur_time += delta per stepper call (HSimulation.tpp:83-84), delta =
+// expiry_k/steps while chain k is the earliest unpriced one
+// (AsianContract.h:35-38), payment when cur_time >= expiry_k
+// (HSimulation.tpp:36, SDE.h:30), possibly several chains on one step.
+static int build_schedule(const double* expiries, uint32_t n_chains, uint32_t steps,
+                          hexo_segment* seg) {
+  if (!expiries || !seg || n_chains == 0 || steps == 0)
+    return fail(HEXO_ERR_INVALID_ARGUMENT, "schedule: need expiries, n_chains>0, steps>0");
+  if (!(expiries[0] > 0.0) || !std::isfinite(expiries[0]))
+    return fail(HEXO_ERR_NOT_INCREASING, "first expiry must be positive and finite");
+  for (uint32_t k = 1; k < n_chains; ++k)
+    if (!(expiries[k - 1] < expiries[k]) || !std::isfinite(expiries[k]))
+      return fail(HEXO_ERR_NOT_INCREASING, "expiries must be strictly increasing (chain %u)", k);
+  volatile double cur_time = 0.0, prev_time = 0.0;  // volatile: no x87/FMA surprises
+  uint32_t k = 0, since_last = 0;
+  double h = expiries[0] / (double)steps;
+  // ++(sde = initial_state): the first step is taken before any check
+  prev_time = cur_time;
+  cur_time = cur_time + h;
+  since_last = 1;
+  for (;;) {
+    while (k < n_chains && cur_time >= expiries[k]) {
+      seg[k].n_steps = since_last;
+      seg[k].h = h;
+      seg[k].w = (expiries[k] - prev_time) / h;
+      seg[k].expiry = expiries[k];
+      since_last = 0;
+      if (++k < n_chains) h = expiries[k] / (double)steps;
+    }
+    if (k >= n_chains) break;
+    prev_time = cur_time;
+    cur_time = cur_time + h;
+    ++since_last;
+  }
+  return HEXO_OK;
+}
+
+static int check_request(const hexo_price_request* r, bool need_strikes) {
+  if (!r) return fail(HEXO_ERR_INVALID_ARGUMENT, "request is NULL");
+  if (r->n_chains == 0 || !r->expiries) return fail(HEXO_ERR_INVALID_ARGUMENT, "no chains");
+  if (r->steps == 0) return fail(HEXO_ERR_INVALID_ARGUMENT, "steps must be > 0");
+  if (r->payoff != HEXO_PAYOFF_ASIAN && r->payoff != HEXO_PAYOFF_EUROPEAN)
+    return fail(HEXO_ERR_INVALID_ARGUMENT, "unknown payoff %d", r->payoff);
+  if (r->normal_mode != HEXO_NORMAL_F32 && r->normal_mode != HEXO_NORMAL_F64)
+    return fail(HEXO_ERR_INVALID_ARGUMENT, "unknown normal_mode %d", r->normal_mode);
+  if (need_strikes) {
+    if (!r->strike_offsets || !r->strikes)
+      return fail(HEXO_ERR_INVALID_ARGUMENT, "strike_offsets / strikes is NULL");
+    if (r->strike_offsets[0] != 0) return fail(HEXO_ERR_INVALID_ARGUMENT, "strike_offsets[0] != 0");
+    for (uint32_t k = 0; k < r->n_chains; ++k)
+      if (r->strike_offsets[k + 1] < r->strike_offsets[k])
+        return fail(HEXO_ERR_INVALID_ARGUMENT, "strike_offsets must be non-decreasing");
+    if (r->strike_offsets[r->n_chains] == 0) return fail(HEXO_ERR_INVALID_ARGUMENT, "no options");
+    if (r->n_paths == 0) return fail(HEXO_ERR_INVALID_ARGUMENT, "n_paths must be > 0");
+  }
+  return HEXO_OK;
+}
+
+static int build_segments(const hexo_price_request* r, bool with_strikes,
+                          std::vector<SegConst>& out, uint64_t* steps_per_path) {
+  std::vector<hexo_segment> sched(r->n_chains);
+  int rc = build_schedule(r->expiries, r->n_chains, r->steps, sched.data());
+  if (rc) return rc;
+  const double theta = r->p.v_m, rho = r->p.rho, kappa = r->p.kappa, eps = r->p.sigma;
+  out.resize(r->n_chains);
+  uint64_t total = 0;
+  for (uint32_t k = 0; k < r->n_chains; ++k) {
+    SegConst& g = out[k];
+    const double h = sched[k].h;
+    g.h = h;
+    g.w = sched[k].w;
+    g.expiry = sched[k].expiry;
+    g.n_steps = sched[k].n_steps;
+    total += g.n_steps;
+    const double D = exp(-kappa * h);                                   // HSimulation.tpp:58
+    g.D = D;
+    g.c1 = eps * eps * D / kappa * (1 - D);                             // :60
+    g.c2 = theta * eps * eps / (2 * kappa) * (1. - D) * (1. - D);       // :60
+    g.K0 = -rho * kappa * theta / eps * h;                              // :75
+    g.K1 = .5 * h * (kappa * rho / eps - .5) - rho / eps;               // :76
+    g.K2 = .5 * h * (kappa * rho / eps - .5) + rho / eps;               // :77
+    g.K3 = .5 * h * (1 - rho * rho);                                    // :78
+    g.K4 = .5 * h * (1 - rho * rho);                                    // :79
+    g.first_opt = with_strikes ? r->strike_offsets[k] : 0;
+    g.n_strikes = with_strikes ? r->strike_offsets[k + 1] - r->strike_offsets[k] : 0;
+    g.pad = 0;
+  }
+  if (steps_per_path) *steps_per_path = total;
+  return HEXO_OK;
+}
+
+// ---------------------------------------------------------------------------
+// host: a prepared launch ("plan") of the path kernel for one shard
+// ---------------------------------------------------------------------------
+struct Plan {
+  PathArgs args{};
+  int payoff = 0, normal_mode = 0;
+  uint32_t grid = 0, block = 0, smem = 0, n_opts = 0;
+  uint64_t steps_per_path = 0, path_steps = 0, n_streams = 0;
+  void* blob = nullptr;       // [segs | strikes | partials | sums]
+  double* sums_dev = nullptr; // inside blob unless caller-supplied
+};
+
+typedef void (*PathKernel)(const PathArgs);
+static PathKernel pick_kernel(int payoff, int normal_mode) {
+  if (payoff == HEXO_PAYOFF_ASIAN)
+    return normal_mode == HEXO_NORMAL_F64 ? heston_qe_paths_kernel<HEXO_PAYOFF_ASIAN, 1>
+                                          : heston_qe_paths_kernel<HEXO_PAYOFF_ASIAN, 0>;
+  return normal_mode == HEXO_NORMAL_F64 ? heston_qe_paths_kernel<HEXO_PAYOFF_EUROPEAN, 1>
+                                        : heston_qe_paths_kernel<HEXO_PAYOFF_EUROPEAN, 0>;
+}
+
+static uint64_t default_streams(uint64_t n_paths, int n_gpus) {
+  // one wave of resident threads per GPU: 2 blocks x 256 threads per SM
+  const uint64_t per_gpu = (uint64_t)(g_ctx.ready ? g_ctx.sm_count : 148) * 2 * kMaxBlock;
+  uint64_t s = per_gpu * (uint64_t)std::max(n_gpus, 1);
+  if (s > n_paths) s = n_paths;
+  return std::max<uint64_t>(s, 1);
+}
+
+static int plan_destroy(Plan* p, cudaStream_t st) {
+  if (p->blob) cudaFreeAsync(p->blob, st);
+  p->blob = nullptr;
+  return HEXO_OK;
+}
+
+static int plan_create(const hexo_price_request* r, uint64_t stream_begin, uint64_t stream_count,
+                       cudaStream_t st, Plan* p) {
+  int rc = check_request(r, true);
+  if (rc) return rc;
+  rc = ensure_context();
+  if (rc) return rc;
+  if (r->n_streams == 0) return fail(HEXO_ERR_INVALID_ARGUMENT, "n_streams must be set for a shard");
+  if (stream_count == 0 || stream_begin + stream_count > r->n_streams)
+    return fail(HEXO_ERR_INVALID_ARGUMENT, "stream range [%llu,+%llu) outside n_streams=%llu",
+                (unsigned long long)stream_begin, (unsigned long long)stream_count,
+                (unsigned long long)r->n_streams);
+  std::vector<SegConst> segs;
+  rc = build_segments(r, true, segs, &p->steps_per_path);
+  if (rc) return rc;
+  const uint32_t n_opts = r->strike_offsets[r->n_chains];
+  // block size: as many warps as the per-warp option accumulators allow
+  int block = kMaxBlock;
+  while (block >= 32 && path_kernel_smem(block, n_opts) > g_ctx.smem_optin) block >>= 1;
+  if (block < 32)
+    return fail(HEXO_ERR_TOO_LARGE, "%u options need %zu B of shared memory per warp, limit %zu",
+                n_opts, path_kernel_smem(32, n_opts), g_ctx.smem_optin);
+  p->payoff = r->payoff;
+  p->normal_mode = r->normal_mode;
+  p->n_opts = n_opts;
+  p->block = (uint32_t)block;
+  p->smem = (uint32_t)path_kernel_smem(block, n_opts);
+  const uint64_t grid64 = (stream_count + block - 1) / block;
+  if (grid64 > 0x7fffffffull) return fail(HEXO_ERR_TOO_LARGE, "too many streams for one launch");
+  p->grid = (uint32_t)grid64;
+  p->n_streams = r->n_streams;
+  p->path_steps = r->n_paths * (uint64_t)r->steps;
+
+  const size_t seg_bytes = segs.size() * sizeof(SegConst);
+  const size_t strike_bytes = (size_t)n_opts * sizeof(double);
+  const size_t part_bytes = (size_t)p->grid * 2 * n_opts * sizeof(double);
+  const size_t sums_bytes = (size_t)2 * n_opts * sizeof(double);
+  auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  const size_t off_strikes = up(seg_bytes), off_part = off_strikes + up(strike_bytes),
+               off_sums = off_part + up(part_bytes), total = off_sums + up(sums_bytes);
+  HEXO_CUDA(cudaMallocAsync(&p->blob, total, st));
+  unsigned char* base = static_cast<unsigned char*>(p->blob);
+  HEXO_CUDA(cudaMemcpyAsync(base, segs.data(), seg_bytes, cudaMemcpyHostToDevice, st));
+  HEXO_CUDA(cudaMemcpyAsync(base + off_strikes, r->strikes, strike_bytes, cudaMemcpyHostToDevice, st));
+  p->sums_dev = reinterpret_cast<double*>(base + off_sums);
+
+  PathArgs& a = p->args;
+  a.v0 = r->p.v_0;
+  a.theta = r->p.v_m;
+  a.S = r->S;
+  a.lnS = log(r->S);  // HSimulation.tpp:90
+  a.seed = r->seed;
+  a.stream_begin = stream_begin;
+  a.stream_count = stream_count;
+  a.base_paths = r->n_paths / r->n_streams;
+  a.rem_streams = r->n_paths % r->n_streams;
+  a.n_seg = r->n_chains;
+  a.n_opts = n_opts;
+  a.segs = reinterpret_cast<const SegConst*>(base);
+  a.strikes = reinterpret_cast<const double*>(base + off_strikes);
+  a.partials = reinterpret_cast<double*>(base + off_part);
+
+  PathKernel kern = pick_kernel(p->payoff, p->normal_mode);
+  HEXO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem));
+  return HEXO_OK;
+}
+
+// enqueue path kernel + reduction; sums land in `sums_out_dev` (or the plan's own buffer)
+static int plan_launch(const Plan* p, cudaStream_t st, double* sums_out_dev) {
+  PathKernel kern = pick_kernel(p->payoff, p->normal_mode);
+  kern<<<p->grid, p->block, p->smem, st>>>(p->args);
+  HEXO_CUDA(cudaGetLastError());
+  const uint32_t n2 = 2 * p->n_opts;
+  reduce_partials_kernel<<<(n2 + 127) / 128, 128, 0, st>>>(p->args.partials, p->grid, n2,
+                                                            sums_out_dev ? sums_out_dev : p->sums_dev);
+  HEXO_CUDA(cudaGetLastError());
+  return HEXO_OK;
+}
+
+static void fill_stats(const Plan& p, float ms, hexo_gpu_stats* s) {
+  if (!s) return;
+  s->n_streams = p.n_streams;
+  s->steps_per_path = p.steps_per_path;
+  s->path_steps = p.path_steps;
+  s->grid = p.grid;
+  s->block = p.block;
+  s->smem_bytes = p.smem;
+  s->kernel_launches = 2;
+  s->kernel_ms = ms;
+}
+
+}  // namespace hexo
+
+// ===========================================================================
+// C ABI
+// ===========================================================================
+using namespace hexo;
+
+extern "C" {
+
+int hexo_gpu_abi_version(void) { return HEXO_GPU_ABI_VERSION; }
+
+const char* hexo_gpu_last_error(void) { return g_err; }
+
+int hexo_gpu_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int hexo_gpu_init(int device) {
+  int n = hexo_gpu_device_count();
+  if (n == 0) return fail(HEXO_ERR_NO_DEVICE, "no CUDA device visible");
+  if (device < 0 || device >= n)
+    return fail(HEXO_ERR_INVALID_ARGUMENT, "device %d out of range [0,%d)", device, n);
+  HEXO_CUDA(cudaSetDevice(device));
+  g_ctx.ready = false;
+  return ensure_context();
+}
+
+int hexo_gpu_shutdown(void) {
+  g_ctx.ready = false;
+  return HEXO_OK;
+}
+
+int hexo_gpu_schedule(const double* expiries, uint32_t n_chains, uint32_t steps,
+                      hexo_segment* segments_out) {
+  return build_schedule(expiries, n_chains, steps, segments_out);
+}
+
+uint64_t hexo_gpu_default_streams(uint64_t n_paths, uint32_t n_opts, int n_gpus) {
+  (void)n_opts;
+  ensure_context();
+  return default_streams(n_paths, n_gpus);
+}
+
+int hexo_gpu_price_shard_device(const hexo_price_request* req, uint64_t stream_begin,
+                                uint64_t stream_count, double* sums_device, void* cuda_stream,
+                                hexo_gpu_stats* stats) {
+  if (!sums_device) return fail(HEXO_ERR_INVALID_ARGUMENT, "sums_device is NULL");
+  cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+  Plan p;
+  int rc = plan_create(req, stream_begin, stream_count, st, &p);
+  if (rc) return rc;
+  rc = plan_launch(&p, st, sums_device);
+  plan_destroy(&p, st);  // stream-ordered free: runs after the kernels
+  fill_stats(p, 0.f, stats);
+  return rc;
+}
+
+int hexo_gpu_price_shard(const hexo_price_request* req, uint64_t stream_begin,
+                         uint64_t stream_count, double* sums_out, hexo_gpu_stats* stats) {
+  if (!sums_out) return fail(HEXO_ERR_INVALID_ARGUMENT, "sums_out is NULL");
+  cudaStream_t st = 0;
+  Plan p;
+  int rc = plan_create(req, stream_begin, stream_count, st, &p);
+  if (rc) return rc;
+  cudaEvent_t e0, e1;
+  HEXO_CUDA(cudaEventCreate(&e0));
+  HEXO_CUDA(cudaEventCreate(&e1));
+  HEXO_CUDA(cudaEventRecord(e0, st));
+  rc = plan_launch(&p, st, nullptr);
+  if (rc == HEXO_OK) {
+    cudaEventRecord(e1, st);
+    cudaError_t e = cudaMemcpyAsync(sums_out, p.sums_dev, (size_t)2 * p.n_opts * sizeof(double),
+                                    cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) rc = fail(HEXO_ERR_CUDA, "path kernel failed: %s", cudaGetErrorString(e));
+  }
+  float ms = 0.f;
+  if (rc == HEXO_OK) cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  plan_destroy(&p, st);
+  fill_stats(p, ms, stats);
+  return rc;
+}
+
+int hexo_gpu_price(const hexo_price_request* req, double* prices_out, double* stderr_out,
+                   hexo_gpu_stats* stats) {
+  int rc = check_request(req, true);
+  if (rc) return rc;
+  if (!prices_out) return fail(HEXO_ERR_INVALID_ARGUMENT, "prices_out is NULL");
+  rc = ensure_context();
+  if (rc) return rc;
+  hexo_price_request r = *req;
+  if (r.n_streams == 0) r.n_streams = default_streams(r.n_paths, 1);
+  const uint32_t n_opts = r.strike_offsets[r.n_chains];
+  std::vector<double> sums(2 * (size_t)n_opts);
+  rc = hexo_gpu_price_shard(&r, 0, r.n_streams, sums.data(), stats);
+  if (rc) return rc;
+  const double n = (double)r.n_paths;
+  for (uint32_t j = 0; j < n_opts; ++j) {
+    const double mean = sums[j] / n;  // HSimulation.tpp:40 divides by n_simulations
+    prices_out[j] = mean;
+    if (stderr_out) {
+      const double var = n > 1 ? std::max(0.0, (sums[n_opts + j] - n * mean * mean) / (n - 1)) : 0.0;
+      stderr_out[j] = sqrt(var / n);
+    }
+  }
+  return HEXO_OK;
+}
+
+int hexo_gpu_shishua_streams(uint64_t seed, uint64_t first_stream, uint32_t n_streams,
+                             uint8_t* bytes_out, size_t bytes_per_stream) {
+  if (!bytes_out || n_streams == 0 || bytes_per_stream == 0 || (bytes_per_stream & 127))
+    return fail(HEXO_ERR_INVALID_ARGUMENT, "shishua: need a buffer and a multiple of 128 bytes");
+  int rc = ensure_context();
+  if (rc) return rc;
+  uint64_t* d = nullptr;
+  const size_t total = (size_t)n_streams * bytes_per_stream;
+  HEXO_CUDA(cudaMalloc(&d, total));
+  shishua_streams_kernel<<<(n_streams + 63) / 64, 64>>>(seed, first_stream, 0, 0, n_streams, d,
+                                                        bytes_per_stream / 8);
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpy(bytes_out, d, total, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  if (e != cudaSuccess) return fail(HEXO_ERR_CUDA, "shishua kernel: %s", cudaGetErrorString(e));
+  return HEXO_OK;
+}
+
+int hexo_gpu_shishua_fill(const uint64_t seed[4], uint8_t* bytes_out, size_t n_bytes) {
+  if (!seed || !bytes_out || n_bytes == 0 || (n_bytes & 127))
+    return fail(HEXO_ERR_INVALID_ARGUMENT, "shishua: need a buffer and a multiple of 128 bytes");
+  int rc = ensure_context();
+  if (rc) return rc;
+  uint64_t* d = nullptr;
+  HEXO_CUDA(cudaMalloc(&d, n_bytes));
+  shishua_streams_kernel<<<1, 32>>>(seed[0], seed[1], seed[2], seed[3], 1, d, n_bytes / 8);
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpy(bytes_out, d, n_bytes, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  if (e != cudaSuccess) return fail(HEXO_ERR_CUDA, "shishua kernel: %s", cudaGetErrorString(e));
+  return HEXO_OK;
+}
+
+int hexo_gpu_u64_to_unit(const uint64_t* bits_in, double* u_out, size_t n) {
+  if (!bits_in || !u_out || n == 0) return fail(HEXO_ERR_INVALID_ARGUMENT, "u64_to_unit: bad args");
+  int rc = ensure_context();
+  if (rc) return rc;
+  uint64_t* din = nullptr;
+  double* dout = nullptr;
+  HEXO_CUDA(cudaMalloc(&din, n * 8));
+  HEXO_CUDA(cudaMalloc(&dout, n * 8));
+  cudaError_t e = cudaMemcpy(din, bits_in, n * 8, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    u64_to_unit_kernel<<<(unsigned)((n + 255) / 256), 256>>>(din, dout, n);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpy(u_out, dout, n * 8, cudaMemcpyDeviceToHost);
+  cudaFree(din);
+  cudaFree(dout);
+  if (e != cudaSuccess) return fail(HEXO_ERR_CUDA, "u64_to_unit: %s", cudaGetErrorString(e));
+  return HEXO_OK;
+}
+
+int hexo_gpu_ppnd16(const double* u_in, double* z_out, size_t n, int normal_mode) {
+  if (!u_in || !z_out || n == 0) return fail(HEXO_ERR_INVALID_ARGUMENT, "ppnd16: bad args");
+  if (normal_mode != HEXO_NORMAL_F32 && normal_mode != HEXO_NORMAL_F64)
+    return fail(HEXO_ERR_INVALID_ARGUMENT, "unknown normal_mode %d", normal_mode);
+  int rc = ensure_context();
+  if (rc) return rc;
+  double *din = nullptr, *dout = nullptr;
+  HEXO_CUDA(cudaMalloc(&din, n * 8));
+  HEXO_CUDA(cudaMalloc(&dout, n * 8));
+  cudaError_t e = cudaMemcpy(din, u_in, n * 8, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    const unsigned grid = (unsigned)((n + 255) / 256);
+    if (normal_mode == HEXO_NORMAL_F64)
+      ppnd16_kernel<1><<<grid, 256>>>(din, dout, n);
+    else
+      ppnd16_kernel<0><<<grid, 256>>>(din, dout, n);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpy(z_out, dout, n * 8, cudaMemcpyDeviceToHost);
+  cudaFree(din);
+  cudaFree(dout);
+  if (e != cudaSuccess) return fail(HEXO_ERR_CUDA, "ppnd16: %s", cudaGetErrorString(e));
+  return HEXO_OK;
+}
+
+int hexo_gpu_replay(const hexo_price_request* req, const double* tape, uint64_t n_paths,
+                    uint32_t tape_steps, double* finals_out) {
+  int rc = check_request(req, false);
+  if (rc) return rc;
+  if (!tape || !finals_out || n_paths == 0)
+    return fail(HEXO_ERR_INVALID_ARGUMENT, "replay: tape / finals_out / n_paths");
+  std::vector<SegConst> segs;
+  uint64_t steps_per_path = 0;
+  rc = build_segments(req, false, segs, &steps_per_path);
+  if (rc) return rc;
+  if (steps_per_path > tape_steps)
+    return fail(HEXO_ERR_TAPE_TOO_SHORT, "schedule needs %llu steps per path, tape has %u",
+                (unsigned long long)steps_per_path, tape_steps);
+  rc = ensure_context();
+  if (rc) return rc;
+  const size_t tape_bytes = (size_t)n_paths * tape_steps * 3 * sizeof(double);
+  const size_t fin_bytes = (size_t)n_paths * req->n_chains * sizeof(double);
+  SegConst* dseg = nullptr;
+  double *dtape = nullptr, *dfin = nullptr;
+  HEXO_CUDA(cudaMalloc(&dseg, segs.size() * sizeof(SegConst)));
+  HEXO_CUDA(cudaMalloc(&dtape, tape_bytes));
+  HEXO_CUDA(cudaMalloc(&dfin, fin_bytes));
+  cudaError_t e = cudaMemcpy(dseg, segs.data(), segs.size() * sizeof(SegConst), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(dtape, tape, tape_bytes, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    const unsigned grid = (unsigned)((n_paths + 127) / 128);
+    if (req->payoff == HEXO_PAYOFF_ASIAN)
+      qe_replay_kernel<HEXO_PAYOFF_ASIAN><<<grid, 128>>>(req->p.v_0, req->p.v_m, req->S, log(req->S),
+                                                         req->n_chains, dseg, dtape, n_paths,
+                                                         tape_steps, dfin);
+    else
+      qe_replay_kernel<HEXO_PAYOFF_EUROPEAN><<<grid, 128>>>(req->p.v_0, req->p.v_m, req->S,
+                                                            log(req->S), req->n_chains, dseg, dtape,
+                                                            n_paths, tape_steps, dfin);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpy(finals_out, dfin, fin_bytes, cudaMemcpyDeviceToHost);
+  cudaFree(dseg);
+  cudaFree(dtape);
+  cudaFree(dfin);
+  if (e != cudaSuccess) return fail(HEXO_ERR_CUDA, "replay: %s", cudaGetErrorString(e));
+  return (int)steps_per_path;
+}
+
+int hexo_gpu_measure_fp64_peak(double* flops_out, float* ms_out) {
+  if (!flops_out) return fail(HEXO_ERR_INVALID_ARGUMENT, "flops_out is NULL");
+  int rc = ensure_context();
+  if (rc) return rc;
+  const int block = 256, grid = g_ctx.sm_count * 8, iters = 4096;
+  double* d = nullptr;
+  HEXO_CUDA(cudaMalloc(&d, (size_t)grid * block * sizeof(double)));
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  float best = 1e30f;
+  for (int rep = 0; rep < 5; ++rep) {
+    cudaEventRecord(e0);
+    dfma_peak_kernel<<<grid, block>>>(d, iters, 1.0000001, 1e-9);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (rep > 0 && ms < best) best = ms;
+  }
+  cudaError_t e = cudaGetLastError();
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d);
+  if (e != cudaSuccess) return fail(HEXO_ERR_CUDA, "dfma peak: %s", cudaGetErrorString(e));
+  const double fmas = (double)grid * block * (double)iters * 64.0;
+  *flops_out = 2.0 * fmas / (best * 1e-3);
+  if (ms_out) *ms_out = best;
+  return HEXO_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,175 @@
+"""Host side of the drop-in: the reference's `HSimulation::price<Scheme>` call
+(src/inc/HSimulation.h:61-63, src/HSimulation.tpp:10-51) with the same argument
+meaning, served by the CUDA path through the C ABI (include/hexo_gpu.h).
+
+    price(HQEAnderson(AAsianCallNonAdaptive), p, S, all_chains, 100000, n_opts, 1000)
+
+mirrors src/Main.cpp:88.  There is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from .types import HParams, OptionsChain, flatten_chains
+
+
+class AAsianCallNonAdaptive:
+    """Arithmetic-average Asian call, trapezoid rule (src/inc/AsianContract.h:14-48)."""
+    payoff = _lib.PAYOFF_ASIAN
+
+
+class EuropeanCallNonAdaptive:
+    """European call (src/inc/VanillaContract.h:14-40)."""
+    payoff = _lib.PAYOFF_EUROPEAN
+
+
+@dataclass(frozen=True)
+class HQEAnderson:
+    """Scheme = Andersen QE stepper + an option policy (src/inc/HSimulation.h:22-47)."""
+    policy: type
+
+    @property
+    def payoff(self) -> int:
+        return self.policy.payoff
+
+
+_NORMAL_MODES = {"f32": _lib.NORMAL_F32, "as-built": _lib.NORMAL_F32, "f64": _lib.NORMAL_F64,
+                 _lib.NORMAL_F32: _lib.NORMAL_F32, _lib.NORMAL_F64: _lib.NORMAL_F64}
+
+
+@dataclass
+class PriceResult:
+    prices: np.ndarray        # [n_opts], chain-major like the reference's vector
+    stderr: np.ndarray        # [n_opts] Monte-Carlo standard errors
+    sums: np.ndarray          # [2*n_opts] raw sum(payoff), sum(payoff^2)
+    n_paths: int
+    n_streams: int
+    steps_per_path: int
+    path_steps: int
+    kernel_ms: float
+    grid: int = 0
+    block: int = 0
+
+
+class _Request:
+    """Keeps the numpy buffers a hexo_price_request points to alive."""
+
+    def __init__(self, scheme, p: HParams, S: float, all_chains: Sequence[OptionsChain],
+                 n_simulations: int, n_opts: Optional[int], steps: int, seed: int, normal_mode,
+                 n_streams: int):
+        if isinstance(scheme, type) and hasattr(scheme, "payoff"):
+            scheme = HQEAnderson(scheme)
+        self.expiries, self.offsets, self.strikes = flatten_chains(all_chains)
+        self.n_opts = int(self.offsets[-1])
+        if n_opts is not None and int(n_opts) != self.n_opts:
+            # the reference trusts the caller (src/Main.cpp:53-57 computes it); be strict
+            raise ValueError(f"n_opts={n_opts} but the chains hold {self.n_opts} options")
+        if normal_mode not in _NORMAL_MODES:
+            raise ValueError(f"normal_mode must be 'f32' or 'f64', got {normal_mode!r}")
+        self.req = _lib.HexoPriceRequest(
+            _lib.HexoHParams(*p.as_tuple()), float(S), scheme.payoff, len(self.expiries),
+            self.expiries.ctypes.data_as(_lib.c_double_p),
+            self.offsets.ctypes.data_as(_lib.c_uint32_p),
+            self.strikes.ctypes.data_as(_lib.c_double_p),
+            int(n_simulations), int(steps), int(seed), _NORMAL_MODES[normal_mode], int(n_streams))
+
+
+def _finish(sums: np.ndarray, n_paths: int, n_opts: int):
+    n = float(n_paths)
+    mean = sums[:n_opts] / n                      # HSimulation.tpp:40 divides by n_simulations
+    if n_paths > 1:
+        var = np.maximum(0.0, (sums[n_opts:] - n * mean * mean) / (n - 1.0))
+    else:
+        var = np.zeros(n_opts)
+    return mean, np.sqrt(var / n)
+
+
+def price_full(scheme, p: HParams, S: float, all_chains: Sequence[OptionsChain],
+               n_simulations: int, n_opts: Optional[int], steps: int, *, seed: int = 1,
+               normal_mode="f32", n_streams: int = 0, device: Optional[int] = None) -> PriceResult:
+    """price<Scheme>() on one GPU, returning prices, standard errors and launch statistics."""
+    lib = _lib.load()
+    if device is not None:
+        _lib.check(lib.hexo_gpu_init(int(device)))
+    rq = _Request(scheme, p, S, all_chains, n_simulations, n_opts, steps, seed, normal_mode, n_streams)
+    if rq.req.n_streams == 0:
+        rq.req.n_streams = lib.hexo_gpu_default_streams(rq.req.n_paths, rq.n_opts, 1)
+    sums = np.zeros(2 * rq.n_opts, dtype=np.float64)
+    stats = _lib.HexoGpuStats()
+    _lib.check(lib.hexo_gpu_price_shard(C.byref(rq.req), 0, rq.req.n_streams,
+                                        sums.ctypes.data_as(_lib.c_double_p), C.byref(stats)))
+    mean, se = _finish(sums, int(n_simulations), rq.n_opts)
+    return PriceResult(mean, se, sums, int(n_simulations), int(stats.n_streams),
+                       int(stats.steps_per_path), int(stats.path_steps), float(stats.kernel_ms),
+                       int(stats.grid), int(stats.block))
+
+
+def price(scheme, p: HParams, S: float, all_chains: Sequence[OptionsChain], n_simulations: int,
+          n_opts: Optional[int], steps: int, **kw) -> np.ndarray:
+    """Drop-in for HSimulation::price<Scheme>: returns the n_opts prices, chain-major."""
+    return price_full(scheme, p, S, all_chains, n_simulations, n_opts, steps, **kw).prices
+
+
+def shard_range(n_streams: int, rank: int, world_size: int):
+    """Contiguous stream range of `rank`: the job's streams split as evenly as possible."""
+    base, rem = divmod(int(n_streams), int(world_size))
+    begin = rank * base + min(rank, rem)
+    return begin, base + (1 if rank < rem else 0)
+
+
+def price_distributed(scheme, p: HParams, S: float, all_chains: Sequence[OptionsChain],
+                      n_simulations: int, n_opts: Optional[int], steps: int, *, seed: int = 1,
+                      normal_mode="f32", n_streams: int = 0, group=None,
+                      _shard_sums=None) -> PriceResult:
+    """price<Scheme>() sharded over the ranks of a torch.distributed group.
+
+    Every rank runs a disjoint range of RNG streams on its own GPU and the
+    2*n_opts payoff sums are combined with ONE all-reduce (NCCL over NVLink when
+    the group's backend is nccl).  All ranks return the same prices.  `_shard_sums`
+    (tests only) replaces the GPU shard computation so the sharding logic can be
+    exercised with gloo on CPU.
+    """
+    import torch
+    import torch.distributed as dist
+
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    rq = _Request(scheme, p, S, all_chains, n_simulations, n_opts, steps, seed, normal_mode, n_streams)
+    stats = _lib.HexoGpuStats()
+    if _shard_sums is None:
+        lib = _lib.load()
+        dev = torch.cuda.current_device()
+        _lib.check(lib.hexo_gpu_init(dev))
+        if rq.req.n_streams == 0:
+            rq.req.n_streams = lib.hexo_gpu_default_streams(rq.req.n_paths, rq.n_opts, world)
+        begin, count = shard_range(rq.req.n_streams, rank, world)
+        sums_t = torch.zeros(2 * rq.n_opts, dtype=torch.float64, device=f"cuda:{dev}")
+        if count > 0:
+            stream = torch.cuda.current_stream().cuda_stream
+            _lib.check(lib.hexo_gpu_price_shard_device(
+                C.byref(rq.req), begin, count, C.c_void_p(sums_t.data_ptr()), C.c_void_p(stream),
+                C.byref(stats)))
+    else:
+        if rq.req.n_streams == 0:
+            raise ValueError("n_streams must be given with a custom shard function")
+        begin, count = shard_range(rq.req.n_streams, rank, world)
+        sums_t = torch.from_numpy(np.asarray(_shard_sums(rq, begin, count), dtype=np.float64).copy())
+    dist.all_reduce(sums_t, op=dist.ReduceOp.SUM, group=group)
+    sums = sums_t.cpu().numpy()
+    mean, se = _finish(sums, int(n_simulations), rq.n_opts)
+    return PriceResult(mean, se, sums, int(n_simulations), int(rq.req.n_streams),
+                       int(stats.steps_per_path), int(n_simulations) * int(steps), 0.0,
+                       int(stats.grid), int(stats.block))
+
+
+def schedule(expiries: Sequence[float], steps: int):
+    """Step schedule of a price<>() call (host only): list of (n_steps, h, w, expiry)."""
+    lib = _lib.load()
+    ex = np.ascontiguousarray(expiries, dtype=np.float64)
+    seg = (_lib.HexoSegment * len(ex))()
+    _lib.check(lib.hexo_gpu_schedule(ex.ctypes.data_as(_lib.c_double_p), len(ex), int(steps), seg))
+    return [(s.n_steps, s.h, s.w, s.expiry) for s in seg]

@@ -1,0 +1,171 @@
+/*
+ * include/hexo_gpu.h -- C ABI of the B200-native Heston Monte-Carlo hot path.
+ *
+ * Drop-in boundary for MartinErhardt/HestonExotics ("hexo").  The reference has
+ * no FFI: the "API" of its MC path is one C++ template,
+ *     HSimulation::price<Scheme>(const HParams&, ffloat S,
+ *         const std::list<options_chain>&, unsigned n_simulations,
+ *         unsigned n_opts, unsigned steps) -> std::vector<ffloat>
+ * (declared src/inc/HSimulation.h:61-63, defined src/HSimulation.tpp:10-51,
+ * only production call site src/Main.cpp:88).  This header is what a binding
+ * for that call binds; hestonexotics_b200/cpp/hexo_gpu_adapter.hpp wraps it
+ * back into the template signature.
+ *
+ * Conventions: plain pointers and sizes, no exceptions across the boundary.
+ * Every function returns HEXO_OK (0) or a negative hexo_status;
+ * hexo_gpu_last_error() gives the message for the calling thread.  All buffers
+ * are caller-owned HOST memory unless the name says `_device`.  There is no CPU
+ * fallback: without a CUDA device every compute entry point fails with
+ * HEXO_ERR_NO_DEVICE.
+ */
+#ifndef HEXO_GPU_H
+#define HEXO_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HEXO_GPU_ABI_VERSION 1
+
+typedef enum {
+  HEXO_OK = 0,
+  HEXO_ERR_INVALID_ARGUMENT = -1, /* NULL pointer, zero size, bad enum            */
+  HEXO_ERR_NOT_INCREASING = -2,   /* expiries not strictly increasing; the         */
+                                  /* reference asserts this, HSimulation.tpp:15-21 */
+  HEXO_ERR_NO_DEVICE = -3,        /* no usable CUDA device                         */
+  HEXO_ERR_CUDA = -4,             /* a CUDA runtime call or kernel failed          */
+  HEXO_ERR_TOO_LARGE = -5,        /* n_opts does not fit the kernel's shared memory */
+  HEXO_ERR_TAPE_TOO_SHORT = -6    /* replay tape has fewer steps than the schedule */
+} hexo_status;
+
+/* Scheme template argument of price<>: which OptionPolicy is plugged into
+ * HQEAnderson (src/inc/AsianContract.h:14-48, src/inc/VanillaContract.h:14-40). */
+typedef enum { HEXO_PAYOFF_ASIAN = 0, HEXO_PAYOFF_EUROPEAN = 1 } hexo_payoff;
+
+/* Arithmetic of the inverse normal.  F32 is what the reference computes AS
+ * BUILT: src/as241.f90:20-25 declares every local and coefficient default REAL
+ * and nothing in Makefile.am promotes them.  F64 is the documented AS241
+ * accuracy ("1 part in 10**16", as241.f90:4). */
+typedef enum { HEXO_NORMAL_F32 = 0, HEXO_NORMAL_F64 = 1 } hexo_normal_mode;
+
+/* HParams, src/inc/HDistribution.h:9-24 -- same field order, same meaning */
+typedef struct {
+  double v_0;   /* initial variance            */
+  double v_m;   /* long-term variance (theta)  */
+  double rho;   /* spot/variance correlation   */
+  double kappa; /* mean-reversion rate         */
+  double sigma; /* vol of variance (epsilon)   */
+} hexo_hparams;
+
+/* One price<Scheme>() call.  std::list<options_chain> (src/inc/Types.h:37-58) is
+ * flattened: chain k has expiry expiries[k] and strikes
+ * strikes[strike_offsets[k] .. strike_offsets[k+1]).  n_opts is
+ * strike_offsets[n_chains].  Output order = the reference's: chain-major, then
+ * option order (HSimulation.tpp:39-40). */
+typedef struct {
+  hexo_hparams p;
+  double S;                       /* spot, `S` of price<>                       */
+  int32_t payoff;                 /* hexo_payoff                                */
+  uint32_t n_chains;
+  const double *expiries;         /* [n_chains] options_chain::time_to_expiry   */
+  const uint32_t *strike_offsets; /* [n_chains+1]                               */
+  const double *strikes;          /* [n_opts] option::strike                    */
+  uint64_t n_paths;               /* `n_simulations` (the reference: unsigned)  */
+  uint32_t steps;                 /* `steps`: step width = expiry/steps         */
+  uint64_t seed;                  /* stream s is shishua seeded {seed,s,0,0}    */
+  int32_t normal_mode;            /* hexo_normal_mode                           */
+  uint64_t n_streams;             /* independent RNG streams the n_paths are    */
+                                  /* split over; 0 = pick for the device(s).    */
+                                  /* For a fixed (seed,n_paths,n_streams) the   */
+                                  /* sums do not depend on how streams are      */
+                                  /* sharded over GPUs.                         */
+} hexo_price_request;
+
+typedef struct {
+  uint64_t n_streams;      /* streams actually used for the whole job          */
+  uint64_t steps_per_path; /* stepper invocations per path (N*, e.g. 253)      */
+  uint64_t path_steps;     /* n_paths x `steps` of this call (metric unit)     */
+  uint32_t grid, block;    /* launch geometry of the path kernel               */
+  uint32_t smem_bytes;
+  uint32_t kernel_launches; /* kernels this call launched                      */
+  float kernel_ms;          /* CUDA-event time of the path kernel + finalize   */
+} hexo_gpu_stats;
+
+/* Step schedule of one price<>() call: the reference advances time by repeated
+ * double addition and compares with the expiry (HSimulation.tpp:35-36,83-84,
+ * SDE.h:30), so the number of steps and the final interpolation weight are a
+ * property of (expiries, steps) in double arithmetic.  Host-only, no GPU. */
+typedef struct {
+  uint32_t n_steps; /* stepper invocations made while heading for this expiry  */
+  double h;         /* step width = expiry/steps (AsianContract.h:35-38)       */
+  double w;         /* (expiry - prev_time)/h at the paying step (:31-32)      */
+  double expiry;
+} hexo_segment;
+
+/* ---- lifecycle ------------------------------------------------------------ */
+int hexo_gpu_abi_version(void);
+/* select the CUDA device for the calling process (one process per GPU) */
+int hexo_gpu_init(int device);
+int hexo_gpu_shutdown(void);
+int hexo_gpu_device_count(void);
+const char *hexo_gpu_last_error(void);
+
+/* ---- host-side schedule (no GPU needed) ------------------------------------ */
+int hexo_gpu_schedule(const double *expiries, uint32_t n_chains, uint32_t steps,
+                      hexo_segment *segments_out /* [n_chains] */);
+
+/* ---- K1: the fused pricing path --------------------------------------------
+ * Replaces HSimulation::price<Scheme> (HSimulation.tpp:10-51).  prices_out
+ * [n_opts] = sum(payoff)/n_paths (:40).  stderr_out (or NULL) = Monte-Carlo
+ * standard error per option, which the reference does not report. */
+int hexo_gpu_price(const hexo_price_request *req, double *prices_out, double *stderr_out,
+                   hexo_gpu_stats *stats);
+
+/* The same path for one shard of the job: streams [stream_begin,
+ * stream_begin+stream_count) of req->n_streams (which must be non-zero here).
+ * sums_out[0..n_opts) = sum of payoffs, sums_out[n_opts..2 n_opts) = sum of
+ * squared payoffs over this shard's paths; summing shards (e.g. by an
+ * all-reduce) and dividing by n_paths gives the price. */
+int hexo_gpu_price_shard(const hexo_price_request *req, uint64_t stream_begin,
+                         uint64_t stream_count, double *sums_out, hexo_gpu_stats *stats);
+
+/* Same, asynchronous: enqueues on `cuda_stream` (a cudaStream_t, 0 = default)
+ * and leaves the 2*n_opts sums in DEVICE memory at sums_device, ready for an
+ * NCCL all-reduce on the same stream.  No host synchronisation. */
+int hexo_gpu_price_shard_device(const hexo_price_request *req, uint64_t stream_begin,
+                                uint64_t stream_count, double *sums_device, void *cuda_stream,
+                                hexo_gpu_stats *stats);
+
+/* default stream count for a job on `n_gpus` devices like the current one */
+uint64_t hexo_gpu_default_streams(uint64_t n_paths, uint32_t n_opts, int n_gpus);
+
+/* ---- K2: raw shishua bytes (replaces prng_init + prng_gen, RNG.cpp:24,29) --- */
+int hexo_gpu_shishua_fill(const uint64_t seed[4], uint8_t *bytes_out, size_t n_bytes);
+/* many streams at once: stream i is seeded {seed, first_stream+i, 0, 0};
+ * bytes_out[i*bytes_per_stream ...] (bytes_per_stream multiple of 128) */
+int hexo_gpu_shishua_streams(uint64_t seed, uint64_t first_stream, uint32_t n_streams,
+                             uint8_t *bytes_out, size_t bytes_per_stream);
+
+/* ---- K3: uniform map and inverse normal (RNG.cpp:31, as241.f90:15-119) ------ */
+int hexo_gpu_u64_to_unit(const uint64_t *bits_in, double *u_out, size_t n);
+int hexo_gpu_ppnd16(const double *u_in, double *z_out, size_t n, int normal_mode);
+
+/* ---- K4: tape replay of stepper + payoff policy ------------------------------
+ * tape[path][step][3] = {Z_V, U_V, Z_X} (normals/uniform the reference's RNG
+ * would have handed to HSimulation.tpp:67,72,80).  finals_out[path][chain] =
+ * the policy's final_value (Asian average / interpolated X_T).  Uses
+ * req->{p,S,payoff,n_chains,expiries,steps}; strikes are not needed. */
+int hexo_gpu_replay(const hexo_price_request *req, const double *tape, uint64_t n_paths,
+                    uint32_t tape_steps, double *finals_out);
+
+/* ---- FP64 pipe peak (roofline denominator; not in MEASURED_PEAKS.json) ------
+ * Runs a register-resident DFMA chain kernel; returns FP64 flop/s (FMA = 2). */
+int hexo_gpu_measure_fp64_peak(double *flops_out, float *ms_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HEXO_GPU_H */

@@ -1,0 +1,301 @@
+"""GPU parity tests: every kernel is called through the C ABI
+(include/hexo_gpu.h) and compared with the CPU oracle on the same inputs.
+
+Tolerances:
+  shishua bytes, uniforms ........ bit-exact
+  normals, f64 mode .............. <= 4 ulp-ish (5e-15 relative to max(1,|z|))
+  normals, f32 (as-built) mode ... <= 2e-6 absolute vs the as-built oracle
+  tape replay final values ....... <= 1e-12 relative
+  fused-kernel payoff sums ....... <= 1e-10 relative vs the oracle on the same streams (f64
+                                   normals); <= 1e-4 in as-built f32 mode (single-precision
+                                   rounding of the normals differs between libm and CUDA)
+  prices ......................... within 3.5 Monte-Carlo standard errors of closed form
+"""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+
+import oracle_api as oa
+import hestonexotics_b200 as hx
+from hestonexotics_b200 import _lib
+from heston_cf import heston_call
+
+pytestmark = pytest.mark.gpu
+
+ASIAN = hx.HQEAnderson(hx.AAsianCallNonAdaptive)
+EURO = hx.HQEAnderson(hx.EuropeanCallNonAdaptive)
+P0 = hx.HParams(*oa.DEFAULT_PARAMS)
+
+
+def chains_of(expiries, strikes_per_chain):
+    return [hx.OptionsChain.from_strikes(T, K) for T, K in zip(expiries, strikes_per_chain)]
+
+
+# ---- K2: shishua ---------------------------------------------------------------
+
+@pytest.mark.parametrize("t", range(8))
+def test_shishua_bytes_bit_exact_reference_thread_seeds(gpu, t):
+    """Seeds 1<<tid are what the reference's threads use (HSimulation.tpp:28); 8 MiB each
+    is one full RNG buffer (RNG.cpp:10,29)."""
+    n = (1 << 20) * 8
+    seed = (C.c_uint64 * 4)(1 << t, 0, 0, 0)
+    out = np.zeros(n, dtype=np.uint8)
+    _lib.check(gpu.hexo_gpu_shishua_fill(seed, out.ctypes.data_as(_lib.c_uint8_p), n))
+    assert np.array_equal(out, oa.shishua_bytes((1 << t, 0, 0, 0), n))
+
+
+def test_shishua_bytes_all_seed_slots(gpu):
+    for sd in [(0, 0, 0, 0), (2 ** 64 - 1,) * 4, (1, 2, 3, 4), (0xDEADBEEF, 0, 7, 2 ** 63)]:
+        seed = (C.c_uint64 * 4)(*sd)
+        out = np.zeros(128 * 40, dtype=np.uint8)
+        _lib.check(gpu.hexo_gpu_shishua_fill(seed, out.ctypes.data_as(_lib.c_uint8_p), out.size))
+        assert np.array_equal(out, oa.shishua_bytes(sd, out.size))
+
+
+def test_shishua_stream_convention(gpu):
+    """Stream s of the fused kernel is seeded {seed, s, 0, 0}."""
+    n_streams, nbytes = 70, 128 * 6
+    out = np.zeros(n_streams * nbytes, dtype=np.uint8)
+    _lib.check(gpu.hexo_gpu_shishua_streams(42, 1000, n_streams,
+                                            out.ctypes.data_as(_lib.c_uint8_p), nbytes))
+    for i in (0, 1, 31, 32, 69):
+        assert np.array_equal(out[i * nbytes:(i + 1) * nbytes],
+                              oa.shishua_bytes((42, 1000 + i, 0, 0), nbytes))
+
+
+# ---- K3: uniform map + PPND16 -----------------------------------------------------
+
+def _gpu_unit(gpu, bits):
+    out = np.zeros(len(bits))
+    _lib.check(gpu.hexo_gpu_u64_to_unit(bits.ctypes.data_as(_lib.c_uint64_p),
+                                        out.ctypes.data_as(_lib.c_double_p), len(bits)))
+    return out
+
+
+def _gpu_ppnd(gpu, u, mode):
+    u = np.ascontiguousarray(u, dtype=np.float64)
+    out = np.zeros(len(u))
+    _lib.check(gpu.hexo_gpu_ppnd16(u.ctypes.data_as(_lib.c_double_p),
+                                   out.ctypes.data_as(_lib.c_double_p), len(u), mode))
+    return out
+
+
+def test_uniform_map_bit_exact(gpu):
+    words = oa.shishua_bytes((1, 0, 0, 0), 1 << 16).view(np.uint64).copy()
+    edge = np.array([0, 1, 2 ** 63, 2 ** 64 - 1, 2 ** 64 - 1024, 2 ** 64 - 1025, 2 ** 53 + 1],
+                    dtype=np.uint64)
+    bits = np.concatenate([edge, words])
+    assert np.array_equal(_gpu_unit(gpu, bits), oa.u64_to_unit(bits))
+
+
+def test_ppnd16_f64(gpu):
+    rng = np.random.default_rng(11)
+    u = np.concatenate([rng.random(100000), 10.0 ** -rng.uniform(3, 300, 3000),
+                        1 - 10.0 ** -rng.uniform(3, 15, 3000),
+                        [0.0, 1.0, 0.5, 0.075, 0.925, 0.0749999, 0.9250001]])
+    z = _gpu_ppnd(gpu, u, _lib.NORMAL_F64)
+    ref = oa.ppnd16(u, oa.NORMAL_F64)
+    err = np.abs(z - ref) / np.maximum(1.0, np.abs(ref))
+    assert err.max() <= 5e-15
+    assert z[-7] == 0.0 and z[-6] == 0.0      # p = 0, 1 -> 0 (as241.f90:99-103)
+
+
+def test_ppnd16_f32_as_built(gpu):
+    rng = np.random.default_rng(12)
+    u = np.concatenate([rng.random(100000), [0.0, 1.0, 0.5, 1e-30, 1 - 1e-9]])
+    z = _gpu_ppnd(gpu, u, _lib.NORMAL_F32)
+    ref = oa.ppnd16(u, oa.NORMAL_F32)
+    assert np.abs(z - ref).max() <= 2e-6
+    assert np.array_equal(z, z.astype(np.float32).astype(np.float64))  # single-precision values
+    # and the as-built routine stays within the survey's measured distance of the f64 one
+    assert np.abs(z - oa.ppnd16(u, oa.NORMAL_F64)).max() <= 3e-6
+
+
+# ---- K4: tape replay ----------------------------------------------------------------
+
+REPLAY_CASES = [
+    (oa.ASIAN, [1.0], 252, oa.DEFAULT_PARAMS),
+    (oa.EUROPEAN, [1.0], 252, oa.DEFAULT_PARAMS),
+    (oa.ASIAN, [1.0], 1024, oa.DEFAULT_PARAMS),          # last-trapezoid quirk, w = 1
+    (oa.ASIAN, [0.5, 1.0], 252, oa.DEFAULT_PARAMS),      # step size switches at the first expiry
+    (oa.EUROPEAN, [0.25, 0.26, 1.0], 100, oa.DEFAULT_PARAMS),
+    (oa.ASIAN, [0.25, 0.2501, 0.2502, 0.6], 50, oa.DEFAULT_PARAMS),  # several expiries on one step
+    (oa.ASIAN, [10.0], 2520, oa.STIFF_PARAMS),
+    (oa.ASIAN, [1.0], 64, (0.01, 0.02, -0.3, 0.5, 1.5)),  # exponential branch dominates
+    (oa.EUROPEAN, [1.0], 1, oa.DEFAULT_PARAMS),
+]
+
+
+@pytest.mark.parametrize("payoff,expiries,steps,params", REPLAY_CASES)
+def test_replay_final_values(gpu, payoff, expiries, steps, params):
+    c = oa.Contract(payoff, expiries, [[100.0]] * len(expiries), steps, params)
+    nsteps = c.steps_to_last_expiry()
+    n_paths = 257
+    rng = np.random.default_rng(steps + len(expiries))
+    tape = np.empty((n_paths, nsteps + 3, 3))
+    tape[:, :, 0] = rng.standard_normal((n_paths, nsteps + 3))
+    tape[:, :, 1] = rng.random((n_paths, nsteps + 3))
+    tape[:, :, 2] = rng.standard_normal((n_paths, nsteps + 3))
+    want, used = c.replay(tape)
+    assert used == nsteps
+    rq = hx.pricing._Request(hx.HQEAnderson(hx.AAsianCallNonAdaptive if payoff == oa.ASIAN
+                                            else hx.EuropeanCallNonAdaptive),
+                             hx.HParams(*params), 100.0, chains_of(expiries, [[100.0]] * len(expiries)),
+                             n_paths, None, steps, 1, "f64", 0)
+    got = np.zeros((n_paths, len(expiries)))
+    rc = gpu.hexo_gpu_replay(C.byref(rq.req), tape.ctypes.data_as(_lib.c_double_p), n_paths,
+                             tape.shape[1], got.ctypes.data_as(_lib.c_double_p))
+    assert rc == nsteps, gpu.hexo_gpu_last_error()
+    rel = np.abs(got - want) / np.abs(want)
+    assert rel.max() <= 1e-12, rel.max()
+
+
+def test_replay_tape_too_short(gpu):
+    rq = hx.pricing._Request(ASIAN, P0, 100.0, chains_of([1.0], [[100.0]]), 4, None, 252, 1, "f64", 0)
+    tape = np.zeros((4, 100, 3))
+    out = np.zeros((4, 1))
+    rc = gpu.hexo_gpu_replay(C.byref(rq.req), tape.ctypes.data_as(_lib.c_double_p), 4, 100,
+                             out.ctypes.data_as(_lib.c_double_p))
+    assert rc == -6
+
+
+# ---- K1: the fused kernel vs the oracle on the SAME streams -----------------------------
+
+FUSED_CASES = [
+    ("asian_1", ASIAN, oa.ASIAN, [1.0], [[100.0]], 252, oa.DEFAULT_PARAMS, 3000, 96),
+    ("euro_1", EURO, oa.EUROPEAN, [1.0], [[100.0]], 252, oa.DEFAULT_PARAMS, 3000, 96),
+    ("asian_quirk", ASIAN, oa.ASIAN, [1.0], [[100.0]], 1024, oa.DEFAULT_PARAMS, 700, 100),
+    ("asian_multi", ASIAN, oa.ASIAN, [0.5, 1.0], [[90.0, 100.0], [100.0, 110.0]], 252,
+     oa.DEFAULT_PARAMS, 2001, 300),
+    ("euro_same_step", EURO, oa.EUROPEAN, [0.25, 0.26, 1.0], [[90.0, 100.0], [100.0, 110.0], [95.0]],
+     100, oa.DEFAULT_PARAMS, 2500, 257),
+    ("asian_same_step", ASIAN, oa.ASIAN, [0.25, 0.2501, 0.2502, 0.6],
+     [[95.0], [100.0, 101.0], [99.0], [100.0]], 50, oa.DEFAULT_PARAMS, 2500, 33),
+    ("asian_chain_70_strikes", ASIAN, oa.ASIAN, [0.25, 0.5], [list(np.linspace(70, 130, 70)),
+                                                            list(np.linspace(70, 130, 33))],
+     60, oa.DEFAULT_PARAMS, 1500, 500),
+    ("stiff", ASIAN, oa.ASIAN, [10.0], [[70.0, 100.0, 130.0]], 2520, oa.STIFF_PARAMS, 200, 64),
+    ("exp_branch", ASIAN, oa.ASIAN, [1.0], [[100.0]], 64, (0.01, 0.02, -0.3, 0.5, 1.5), 3000, 128),
+    ("one_stream", ASIAN, oa.ASIAN, [1.0], [[100.0]], 32, oa.DEFAULT_PARAMS, 50, 1),
+    ("more_streams_than_a_block", EURO, oa.EUROPEAN, [0.5], [[100.0]], 16, oa.DEFAULT_PARAMS,
+     5000, 1000),
+]
+
+
+@pytest.mark.parametrize("mode,tol", [("f64", 1e-10), ("f32", 1e-4)])
+@pytest.mark.parametrize("case", FUSED_CASES, ids=[c[0] for c in FUSED_CASES])
+def test_fused_kernel_sums_vs_oracle_streams(gpu, case, mode, tol):
+    _, scheme, payoff, T, K, steps, params, n_paths, n_streams = case
+    c = oa.Contract(payoff, T, K, steps, params)
+    nm = oa.NORMAL_F64 if mode == "f64" else oa.NORMAL_F32
+    sm, sq = c.price_stream(seed=7, n_paths=n_paths, n_streams=n_streams, normal_mode=nm)
+    res = hx.price_full(scheme, hx.HParams(*params), 100.0, chains_of(T, K), n_paths, c.n_opts,
+                        steps, seed=7, normal_mode=mode, n_streams=n_streams)
+    n = c.n_opts
+    scale = np.maximum(np.abs(sm), 1e-300)
+    assert (np.abs(res.sums[:n] - sm) / scale).max() <= tol
+    assert (np.abs(res.sums[n:] - sq) / np.maximum(np.abs(sq), 1e-300)).max() <= 2 * tol
+    assert np.allclose(res.prices, sm / n_paths, rtol=tol)
+    assert res.steps_per_path == c.steps_to_last_expiry()
+    assert res.path_steps == n_paths * steps
+
+
+def test_sharded_streams_add_up(gpu):
+    """Shards of one job (what the ranks of a multi-GPU run compute) sum to the whole."""
+    T, K = [0.5, 1.0], [[95.0, 100.0], [105.0]]
+    rq = hx.pricing._Request(ASIAN, P0, 100.0, chains_of(T, K), 5003, 3, 40, 11, "f64", 37)
+    def shard(b, n):
+        out = np.zeros(6)
+        _lib.check(gpu.hexo_gpu_price_shard(C.byref(rq.req), b, n,
+                                            out.ctypes.data_as(_lib.c_double_p), None))
+        return out
+    whole = shard(0, 37)
+    parts = shard(0, 10) + shard(10, 20) + shard(30, 7)
+    assert np.allclose(whole, parts, rtol=1e-13)
+    c = oa.Contract(oa.ASIAN, T, K, 40)
+    sm, sq = c.price_stream(11, 5003, 37, normal_mode=oa.NORMAL_F64)
+    assert np.allclose(whole, np.concatenate([sm, sq]), rtol=1e-10)
+
+
+def test_run_to_run_reproducible(gpu):
+    a = hx.price_full(ASIAN, P0, 100.0, chains_of([1.0], [[100.0]]), 20000, 1, 252, seed=5)
+    b = hx.price_full(ASIAN, P0, 100.0, chains_of([1.0], [[100.0]]), 20000, 1, 252, seed=5)
+    assert np.array_equal(a.sums, b.sums)
+    c = hx.price_full(ASIAN, P0, 100.0, chains_of([1.0], [[100.0]]), 20000, 1, 252, seed=6)
+    assert not np.array_equal(a.sums, c.sums)
+
+
+# ---- prices: BASELINE.json configs at (or near) full size ---------------------------------
+
+def test_cfg2_european_vs_closed_form(gpu):
+    """cfg2: European call, 1M paths x 252 steps, checked against closed-form Heston (r=0)."""
+    cf = heston_call(100, 100, 1.0, *oa.DEFAULT_PARAMS, r=0.0)
+    for mode in ("f32", "f64"):
+        r = hx.price_full(EURO, P0, 100.0, chains_of([1.0], [[100.0]]), 1_000_000, 1, 252,
+                          seed=1, normal_mode=mode)
+        # QE discretisation bias at 252 steps is below the MC error at 1M paths
+        assert abs(r.prices[0] - cf) <= 3.5 * r.stderr[0], (mode, r.prices[0], cf, r.stderr[0])
+
+
+def test_cfg1_asian_vs_reference_fixture(gpu):
+    """cfg1: Asian call 100k paths x 252 steps; within 3 combined SE of the reference's own
+    estimate (the golden fixture holds 4000 reference paths; SE from the GPU run)."""
+    with open(os.path.join(os.path.dirname(__file__), "golden", "reference_outputs.json")) as f:
+        gold = json.load(f)
+    ref_price = float.fromhex(gold["prices"]["cfg1_asian_252"]["f32"][0])
+    r = hx.price_full(ASIAN, P0, 100.0, chains_of([1.0], [[100.0]]), 100_000, 1, 252, seed=1)
+    se_ref = r.stderr[0] * np.sqrt(100_000 / 4000)
+    assert abs(r.prices[0] - ref_price) <= 3.0 * np.hypot(r.stderr[0], se_ref)
+    # and against a large oracle-convention run summarised as a constant: 4.27 +- 0.01
+    assert abs(r.prices[0] - 4.27) < 0.05
+
+
+def test_cfg4_quirk_bias_is_reproduced(gpu):
+    """1024 steps land exactly on T, so the last trapezoid is replaced (SURVEY finding 6):
+    the Asian price drops from ~4.27 to ~4.22-4.23.  A corrected scheme would fail this."""
+    r = hx.price_full(ASIAN, P0, 100.0, chains_of([1.0], [[100.0]]), 2_000_000, 1, 1024, seed=1)
+    a = hx.price_full(ASIAN, P0, 100.0, chains_of([1.0], [[100.0]]), 2_000_000, 1, 252, seed=1)
+    assert 4.20 < r.prices[0] < 4.245
+    assert a.prices[0] - r.prices[0] > 5 * np.hypot(r.stderr[0], a.stderr[0])
+
+
+def test_cfg3_chain_monotone_and_consistent(gpu):
+    """cfg3 shape: 64 strikes x 8 maturities in one call; call prices fall with the strike and
+    the 8-chain call agrees with a single-chain call of the first maturity within MC error."""
+    T = [0.25 * k for k in range(1, 9)]
+    K = [list(np.linspace(70, 130, 64))] * 8
+    r = hx.price_full(ASIAN, P0, 100.0, chains_of(T, K), 400_000, 512, 252, seed=2)
+    pr = r.prices.reshape(8, 64)
+    assert (np.diff(pr, axis=1) <= 1e-12).all()
+    one = hx.price_full(ASIAN, P0, 100.0, chains_of(T[:1], K[:1]), 400_000, 64, 252, seed=3)
+    z = (pr[0] - one.prices) / np.hypot(r.stderr[:64], one.stderr) 
+    assert np.abs(z[np.isfinite(z)]).max() < 4.5
+
+
+def test_cfg5_stiff_european_vs_closed_form(gpu):
+    """cfg5 parameters (kappa=20, sigma=1, rho=-0.95), T=10, 2520 steps, European leg against the
+    closed form 24.50401."""
+    p = hx.HParams(*oa.STIFF_PARAMS)
+    cf = heston_call(100, 100, 10.0, *oa.STIFF_PARAMS, r=0.0)
+    r = hx.price_full(EURO, p, 100.0, chains_of([10.0], [[100.0]]), 400_000, 1, 2520, seed=1)
+    assert abs(r.prices[0] - cf) <= 3.5 * r.stderr[0]
+
+
+def test_put_call_parity_style_martingale_check(gpu):
+    """Size-independent property: with strike 0 the European payoff is X_T itself, and QE without
+    martingale correction still keeps E[X_T] within a small bias of S (r = 0)."""
+    r = hx.price_full(EURO, P0, 100.0, chains_of([1.0], [[0.0]]), 1_000_000, 1, 252, seed=4)
+    assert abs(r.prices[0] - 100.0) <= 4 * r.stderr[0] + 0.02
+
+
+def test_errors(gpu):
+    with pytest.raises(_lib.HexoGpuError) as e:
+        hx.price(ASIAN, P0, 100.0, chains_of([1.0, 0.5], [[100.0], [100.0]]), 1000, 2, 252)
+    assert e.value.code == -2
+    with pytest.raises(_lib.HexoGpuError) as e:
+        hx.price(ASIAN, P0, 100.0, chains_of([1.0], [list(np.linspace(50, 150, 20000))]), 1000,
+                 20000, 16)
+    assert e.value.code == -5
