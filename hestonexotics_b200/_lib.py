@@ -17,7 +17,8 @@ ABI_SYMBOLS = (
     "hexo_gpu_last_error", "hexo_gpu_schedule", "hexo_gpu_price", "hexo_gpu_price_shard",
     "hexo_gpu_price_shard_device", "hexo_gpu_default_streams", "hexo_gpu_shishua_fill",
     "hexo_gpu_shishua_streams", "hexo_gpu_u64_to_unit", "hexo_gpu_ppnd16", "hexo_gpu_replay",
-    "hexo_gpu_measure_fp64_peak",
+    "hexo_gpu_measure_fp64_peak", "hexo_gpu_plan_create", "hexo_gpu_plan_launch",
+    "hexo_gpu_plan_sums_device", "hexo_gpu_plan_stats", "hexo_gpu_plan_destroy",
 )
 
 HEXO_OK = 0
@@ -86,6 +87,13 @@ def load() -> C.CDLL:
                                          c_double_p, C.POINTER(HexoGpuStats)]
     lib.hexo_gpu_price_shard_device.argtypes = [C.POINTER(HexoPriceRequest), C.c_uint64, C.c_uint64,
                                                 C.c_void_p, C.c_void_p, C.POINTER(HexoGpuStats)]
+    lib.hexo_gpu_plan_create.argtypes = [C.POINTER(HexoPriceRequest), C.c_uint64, C.c_uint64,
+                                         C.POINTER(C.c_void_p)]
+    lib.hexo_gpu_plan_launch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.hexo_gpu_plan_sums_device.argtypes = [C.c_void_p]
+    lib.hexo_gpu_plan_sums_device.restype = C.c_void_p
+    lib.hexo_gpu_plan_stats.argtypes = [C.c_void_p, C.POINTER(HexoGpuStats)]
+    lib.hexo_gpu_plan_destroy.argtypes = [C.c_void_p]
     lib.hexo_gpu_default_streams.argtypes = [C.c_uint64, C.c_uint32, C.c_int]
     lib.hexo_gpu_default_streams.restype = C.c_uint64
     lib.hexo_gpu_shishua_fill.argtypes = [c_uint64_p, c_uint8_p, C.c_size_t]

@@ -587,6 +587,49 @@ uint64_t hexo_gpu_default_streams(uint64_t n_paths, uint32_t n_opts, int n_gpus)
   return default_streams(n_paths, n_gpus);
 }
 
+struct hexo_gpu_plan {
+  Plan p;
+};
+
+int hexo_gpu_plan_create(const hexo_price_request* req, uint64_t stream_begin,
+                         uint64_t stream_count, hexo_gpu_plan** plan_out) {
+  if (!plan_out) return fail(HEXO_ERR_INVALID_ARGUMENT, "plan_out is NULL");
+  hexo_gpu_plan* h = new hexo_gpu_plan();
+  int rc = plan_create(req, stream_begin, stream_count, 0, &h->p);
+  if (rc == HEXO_OK) {
+    cudaError_t e = cudaStreamSynchronize(0);  // inputs resident before the first launch
+    if (e != cudaSuccess) rc = fail(HEXO_ERR_CUDA, "plan upload: %s", cudaGetErrorString(e));
+  }
+  if (rc) {
+    plan_destroy(&h->p, 0);
+    delete h;
+    return rc;
+  }
+  *plan_out = h;
+  return HEXO_OK;
+}
+
+int hexo_gpu_plan_launch(hexo_gpu_plan* plan, double* sums_device, void* cuda_stream) {
+  if (!plan) return fail(HEXO_ERR_INVALID_ARGUMENT, "plan is NULL");
+  return plan_launch(&plan->p, static_cast<cudaStream_t>(cuda_stream), sums_device);
+}
+
+double* hexo_gpu_plan_sums_device(hexo_gpu_plan* plan) { return plan ? plan->p.sums_dev : nullptr; }
+
+int hexo_gpu_plan_stats(const hexo_gpu_plan* plan, hexo_gpu_stats* stats) {
+  if (!plan || !stats) return fail(HEXO_ERR_INVALID_ARGUMENT, "plan / stats is NULL");
+  fill_stats(plan->p, 0.f, stats);
+  return HEXO_OK;
+}
+
+int hexo_gpu_plan_destroy(hexo_gpu_plan* plan) {
+  if (!plan) return HEXO_OK;
+  cudaDeviceSynchronize();
+  plan_destroy(&plan->p, 0);
+  delete plan;
+  return HEXO_OK;
+}
+
 int hexo_gpu_price_shard_device(const hexo_price_request* req, uint64_t stream_begin,
                                 uint64_t stream_count, double* sums_device, void* cuda_stream,
                                 hexo_gpu_stats* stats) {

@@ -139,6 +139,20 @@ int hexo_gpu_price_shard_device(const hexo_price_request *req, uint64_t stream_b
                                 uint64_t stream_count, double *sums_device, void *cuda_stream,
                                 hexo_gpu_stats *stats);
 
+/* ---- prepared launches -------------------------------------------------------
+ * A plan holds everything one shard needs in device memory (segment constants,
+ * strikes, per-block partials, sums), so that repeated launches move no input
+ * data: hexo_gpu_plan_launch only enqueues the path kernel and the reduction on
+ * `cuda_stream`.  sums_device == NULL leaves the sums in the plan's own buffer
+ * (hexo_gpu_plan_sums_device). */
+typedef struct hexo_gpu_plan hexo_gpu_plan;
+int hexo_gpu_plan_create(const hexo_price_request *req, uint64_t stream_begin,
+                         uint64_t stream_count, hexo_gpu_plan **plan_out);
+int hexo_gpu_plan_launch(hexo_gpu_plan *plan, double *sums_device, void *cuda_stream);
+double *hexo_gpu_plan_sums_device(hexo_gpu_plan *plan);
+int hexo_gpu_plan_stats(const hexo_gpu_plan *plan, hexo_gpu_stats *stats);
+int hexo_gpu_plan_destroy(hexo_gpu_plan *plan);
+
 /* default stream count for a job on `n_gpus` devices like the current one */
 uint64_t hexo_gpu_default_streams(uint64_t n_paths, uint32_t n_opts, int n_gpus);
 
