@@ -1,0 +1,83 @@
+// hestonexotics_b200/csrc/fastmath.cuh
+//
+// Branch-free double-precision reciprocal, square root and exponential for the
+// QE step.  CUDA's own `/`, sqrt() and exp() are correctly rounded / <1 ulp but
+// each carries a slow path (denormals, huge arguments) behind a divergent branch
+// and a call; on the path kernel those branches cost more issue slots than the
+// arithmetic.  The versions here start from the 20-bit MUFU seeds
+// (rcp.approx.ftz.f64 / rsqrt.approx.ftz.f64 -> MUFU.RCP64H / MUFU.RSQ64H) and
+// apply ONE third-order correction, which lands within ~1 ulp for the normal,
+// well-scaled arguments the stepper produces (tests/test_gpu_parity.py pins the
+// error through hexo_gpu_selftest_math).
+#pragma once
+#include <stdint.h>
+
+namespace hexo {
+
+__device__ __forceinline__ double mufu_rcp64(double a) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+  return y;
+}
+__device__ __forceinline__ double mufu_rsqrt64(double a) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+  return y;
+}
+
+// 1/a for normal a (not 0, inf, nan, denormal).  y0 has relative error e ~ 2^-20;
+// y0 (1 + e + e^2) leaves e^3 ~ 2^-60.
+__device__ __forceinline__ double fast_rcp(double a) {
+  const double y0 = mufu_rcp64(a);
+  const double e = fma(-a, y0, 1.0);
+  const double t = fma(e, e, e);
+  return fma(y0, t, y0);
+}
+
+// sqrt(a) for normal a > 0.  With g = a y0 and r = 1 - g y0, sqrt(a) = g (1-r)^(-1/2)
+// = g (1 + r/2 + 3 r^2/8 + O(r^3)), r ~ 2^-19.
+__device__ __forceinline__ double fast_sqrt(double a) {
+  const double y0 = mufu_rsqrt64(a);
+  const double g = a * y0;
+  const double r = fma(-g, y0, 1.0);
+  const double q = fma(0.375, r, 0.5);
+  return fma(g, q * r, g);
+}
+
+// sqrt(a) for a >= 0 including exact zero (returns ~1e-150 instead of 0, which the
+// caller multiplies by a normal draw and adds to a log-spot of order 1).
+__device__ __forceinline__ double fast_sqrt_nonneg(double a) {
+  return fast_sqrt(fmax(a, 1e-300));
+}
+
+// exp(x) for |x| < 700: x = (32 k + j) ln2/32 + r, exp(x) = 2^k 2^(j/32) e^r with
+// |r| <= ln2/64 and a degree-6 Taylor polynomial (remainder r^7/5040 < 4e-18).
+// `tab` holds 2^(j/32), j = 0..31 (shared memory, filled by exp_table_init).
+__device__ __forceinline__ double fast_exp(double x, const double* __restrict__ tab) {
+  const double kMagic = 6755399441055744.0;          // 1.5 * 2^52
+  const double kInvL = 46.166241308446828384;        // 32/ln2
+  const double kLhi = 2.16608493865351192653e-02;    // ln2/32, high part (low bits zero)
+  const double kLlo = 5.96317165397058656257e-12;    // ln2/32 - kLhi
+  const double t = fma(x, kInvL, kMagic);
+  const int n = __double2loint(t);                   // round-to-nearest integer of x*32/ln2
+  const double nd = t - kMagic;
+  double r = fma(nd, -kLhi, x);
+  r = fma(nd, -kLlo, r);
+  double p = fma(r, 1.0 / 720.0, 1.0 / 120.0);
+  p = fma(p, r, 1.0 / 24.0);
+  p = fma(p, r, 1.0 / 6.0);
+  p = fma(p, r, 0.5);
+  p = fma(p, r, 1.0);
+  p = p * r;                                         // e^r - 1
+  const double T = tab[n & 31];
+  const double v = fma(T, p, T);
+  // scale by 2^k: add k to the exponent field (v is in [1,2), k in [-1010,1010])
+  const int k = n >> 5;
+  return __hiloint2double(__double2hiint(v) + (k << 20), __double2loint(v));
+}
+
+__device__ __forceinline__ void exp_table_init(double* tab, int tid, int nthreads) {
+  for (int j = tid; j < 32; j += nthreads) tab[j] = exp2((double)j / 32.0);
+}
+
+}  // namespace hexo

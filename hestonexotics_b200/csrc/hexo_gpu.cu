@@ -31,6 +31,7 @@
 #include <vector>
 
 #include "../../include/hexo_gpu.h"
+#include "normals.cuh"
 #include "qe.cuh"
 #include "shishua.cuh"
 
@@ -92,10 +93,10 @@ static int ensure_context() {
 // K1: fused path kernel
 // ---------------------------------------------------------------------------
 constexpr int kMaxBlock = 256;
-constexpr int kRingWords = 16;  // one shishua round
+constexpr int kStepsPerRound = 8;  // one shishua round = 16 words = 8 steps
 
 struct PathArgs {
-  double v0, theta, S, lnS;
+  double v0, S, lnS;
   uint64_t seed;
   uint64_t stream_begin;  // first global stream id of this launch
   uint64_t stream_count;  // streams in this launch (one per thread)
@@ -107,24 +108,102 @@ struct PathArgs {
   double* partials;  // [gridDim.x][2*n_opts]
 };
 
-__host__ __device__ inline size_t path_kernel_smem(int block, uint32_t n_opts) {
+// Shared memory of the path kernel (per block):
+//   zring  [8][T] pairs (Z_V, Z_X) of the current generator round, float2 (F32
+//                 mode) or double2 (F64 mode);   T = threads per block
+//   uring  [8][T] raw variance words of the round (the uniform of the psi >= 1.5
+//                 branch comes from the same word as the normal it replaces)
+//   exptab [32]   2^(j/32)
+//   fvbuf  [W][32] final values of a warp at a maturity;  W = warps per block
+//   acc    [W][2][n_opts] lane-owned payoff sums / sums of squares
+__host__ __device__ inline size_t path_kernel_smem(int block, uint32_t n_opts, int normal_mode) {
   const int warps = block / 32;
-  return (size_t)kRingWords * 8 * block + (size_t)32 * 8 * warps + (size_t)warps * 2 * n_opts * 8;
+  const size_t zbytes = (normal_mode == HEXO_NORMAL_F64 ? 16 : 8) * (size_t)kStepsPerRound * block;
+  return zbytes + (size_t)8 * kStepsPerRound * block + 32 * 8 + (size_t)32 * 8 * warps +
+         (size_t)warps * 2 * n_opts * 8;
 }
+
+template <int NORMAL_MODE>
+struct ZRing;
+
+// F32 mode: both normals of a step in one 8-byte word
+template <>
+struct ZRing<HEXO_NORMAL_F32> {
+  float2* z;  // this thread's column, stride T
+  int T;
+  static constexpr int kBytesPerStep = 8;
+  __device__ __forceinline__ void fill(const uint64_t (&o)[16]) {
+#pragma unroll
+    for (int s = 0; s < kStepsPerRound; ++s) {
+      float zv, zx;
+      normal2_f32(o[2 * s], o[2 * s + 1], zv, zx);
+      z[s * T] = make_float2(zv, zx);
+    }
+  }
+  __device__ __forceinline__ void get(int s, double& zv, double& zx) const {
+    const float2 v = z[s * T];
+    zv = (double)v.x;
+    zx = (double)v.y;
+  }
+};
+
+// F64 mode: central region for every draw, then a per-lane loop over the tails
+template <>
+struct ZRing<HEXO_NORMAL_F64> {
+  double2* z;
+  int T;
+  static constexpr int kBytesPerStep = 16;
+  __device__ __forceinline__ void fill(const uint64_t (&o)[16]) {
+    uint32_t tails = 0;
+#pragma unroll
+    for (int s = 0; s < kStepsPerRound; ++s) {
+      bool t0, t1;
+      const double zv = normal_central_f64(o[2 * s], t0);
+      const double zx = normal_central_f64(o[2 * s + 1], t1);
+      // a tail draw parks its raw word in the slot until the loop below replaces it
+      z[s * T] = make_double2(t0 ? __longlong_as_double((long long)o[2 * s]) : zv,
+                              t1 ? __longlong_as_double((long long)o[2 * s + 1]) : zx);
+      tails |= (t0 ? 1u : 0u) << (2 * s) | (t1 ? 1u : 0u) << (2 * s + 1);
+    }
+    double* zz = reinterpret_cast<double*>(z);
+    while (tails) {
+      const int j = __ffs(tails) - 1;
+      tails &= tails - 1;
+      double* slot = zz + (size_t)(j >> 1) * T * 2 + (j & 1);
+      *slot = normal_tail_f64((uint64_t)__double_as_longlong(*slot));
+    }
+  }
+  __device__ __forceinline__ void get(int s, double& zv, double& zx) const {
+    const double2 v = z[s * T];
+    zv = v.x;
+    zx = v.y;
+  }
+};
 
 template <int PAYOFF, int NORMAL_MODE>
 __global__ void __launch_bounds__(kMaxBlock, 2) heston_qe_paths_kernel(const PathArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int nthreads = blockDim.x, nwarps = nthreads >> 5;
-  uint64_t* ring = reinterpret_cast<uint64_t*>(smem_raw);           // [16][nthreads]
-  double* fvbuf = reinterpret_cast<double*>(ring + kRingWords * nthreads) + 32 * warp;
-  double* acc_all = reinterpret_cast<double*>(ring + kRingWords * nthreads) + 32 * nwarps;
-  double* my_sum = acc_all + (size_t)warp * 2 * a.n_opts;           // lane-owned slots
+  const int T = blockDim.x, nwarps = T >> 5;
+  using Ring = ZRing<NORMAL_MODE>;
+  unsigned char* sp = smem_raw;
+  Ring ring;
+  ring.z = reinterpret_cast<decltype(ring.z)>(sp) + tid;
+  ring.T = T;
+  sp += (size_t)Ring::kBytesPerStep * kStepsPerRound * T;
+  uint64_t* ucol = reinterpret_cast<uint64_t*>(sp) + tid;  // raw variance words, stride T
+  sp += (size_t)8 * kStepsPerRound * T;
+  double* exptab = reinterpret_cast<double*>(sp);
+  sp += 32 * 8;
+  double* fvbuf = reinterpret_cast<double*>(sp) + 32 * warp;
+  sp += (size_t)32 * 8 * nwarps;
+  double* acc_all = reinterpret_cast<double*>(sp);
+  double* my_sum = acc_all + (size_t)warp * 2 * a.n_opts;  // lane-owned slots
   double* my_sq = my_sum + a.n_opts;
   for (uint32_t j = lane; j < 2 * a.n_opts; j += 32) my_sum[j] = 0.0;
+  exp_table_init(exptab, tid, T);
 
-  const uint64_t slot = (uint64_t)blockIdx.x * nthreads + tid;
+  const uint64_t slot = (uint64_t)blockIdx.x * T + tid;
   const uint64_t sid = a.stream_begin + slot;
   const uint64_t my_paths =
       slot < a.stream_count ? a.base_paths + (sid < a.rem_streams ? 1u : 0u) : 0u;
@@ -132,15 +211,15 @@ __global__ void __launch_bounds__(kMaxBlock, 2) heston_qe_paths_kernel(const Pat
   const uint64_t warp_paths = __shfl_sync(0xffffffffu, my_paths, 0);
 
   Shishua rng;
-  uint64_t* col = ring + tid;  // my column: word j at col[j*nthreads]
   {
     uint64_t o[16];
     rng.init(a.seed, sid, 0, 0, o);
 #pragma unroll
-    for (int j = 0; j < 16; ++j) col[j * nthreads] = o[j];
+    for (int s = 0; s < kStepsPerRound; ++s) ucol[s * T] = o[2 * s];
+    ring.fill(o);
   }
-  int pos = 0;
-  __syncwarp();
+  int pos = 0;  // next unread step of the round
+  __syncthreads();  // exptab
 
   for (uint64_t p = 0; p < warp_paths; ++p) {
     const bool active = p < my_paths;
@@ -160,25 +239,26 @@ __global__ void __launch_bounds__(kMaxBlock, 2) heston_qe_paths_kernel(const Pat
         const double Xa = X;
         double sumX = 0.0;
         for (uint32_t i = 0; i < n; ++i) {
-          if (pos == kRingWords) {
+          if (pos == kStepsPerRound) {
             uint64_t o[16];
             rng.round(o);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) col[j * nthreads] = o[j];
+            for (int s = 0; s < kStepsPerRound; ++s) ucol[s * T] = o[2 * s];
+            ring.fill(o);
             pos = 0;
           }
-          WordDraws<NORMAL_MODE> d;
-          d.wv = col[pos * nthreads];
-          d.wx = col[(pos + 1) * nthreads];
-          pos += 2;
-          qe_step(g, a.theta, V, lnX, d);
+          double zv, zx;
+          ring.get(pos, zv, zx);
+          const uint64_t* uword = ucol + pos * T;
+          ++pos;
+          qe_step(g, V, lnX, zv, [uword]() { return u64_to_unit(*uword); }, zx);
           if (PAYOFF == HEXO_PAYOFF_ASIAN) {
             Xprev = X;
-            X = exp(lnX);                    // HSimulation.tpp:81-82
+            X = fast_exp(lnX, exptab);       // HSimulation.tpp:81-82
             if (i + 1 < n) sumX += X;        // all but the crossing step
           } else if (i + 2 >= n) {           // European: X is only read at the expiry
             Xprev = X;
-            X = exp(lnX);
+            X = fast_exp(lnX, exptab);
           }
         }
         if (PAYOFF == HEXO_PAYOFF_ASIAN && n > 0) {
@@ -216,7 +296,7 @@ __global__ void __launch_bounds__(kMaxBlock, 2) heston_qe_paths_kernel(const Pat
   // warps -> block partial, fixed order
   __syncthreads();
   const uint32_t n2 = 2 * a.n_opts;
-  for (uint32_t j = tid; j < n2; j += nthreads) {
+  for (uint32_t j = tid; j < n2; j += T) {
     double s = 0.0;
     for (int w = 0; w < nwarps; ++w) s += acc_all[(size_t)w * n2 + j];
     a.partials[(size_t)blockIdx.x * n2 + j] = s;
@@ -269,9 +349,12 @@ __global__ void ppnd16_kernel(const double* in, double* out, size_t n) {
 // K4: tape replay (one thread per path), same stepper and policy arithmetic
 // ---------------------------------------------------------------------------
 template <int PAYOFF>
-__global__ void qe_replay_kernel(double v0, double theta, double S, double lnS, uint32_t n_seg,
+__global__ void qe_replay_kernel(double v0, double S, double lnS, uint32_t n_seg,
                                  const SegConst* segs, const double* tape, uint64_t n_paths,
                                  uint32_t tape_steps, double* finals) {
+  __shared__ double exptab[32];
+  exp_table_init(exptab, threadIdx.x, blockDim.x);
+  __syncthreads();
   const uint64_t path = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (path >= n_paths) return;
   const double* t = tape + (size_t)path * tape_steps * 3;
@@ -284,15 +367,15 @@ __global__ void qe_replay_kernel(double v0, double theta, double S, double lnS, 
     const double Xa = X;
     double sumX = 0.0;
     for (uint32_t i = 0; i < n; ++i, ++step) {
-      TapeDraws d = {t[3 * step], t[3 * step + 1], t[3 * step + 2]};
-      qe_step(g, theta, V, lnX, d);
+      const double uv = t[3 * step + 1];
+      qe_step(g, V, lnX, t[3 * step], [uv]() { return uv; }, t[3 * step + 2]);
       if (PAYOFF == HEXO_PAYOFF_ASIAN) {
         Xprev = X;
-        X = exp(lnX);
+        X = fast_exp(lnX, exptab);
         if (i + 1 < n) sumX += X;
       } else if (i + 2 >= n) {
         Xprev = X;
-        X = exp(lnX);
+        X = fast_exp(lnX, exptab);
       }
     }
     if (PAYOFF == HEXO_PAYOFF_ASIAN && n > 0) integral += g.h * 0.5 * (Xa - Xprev + 2.0 * sumX);
@@ -399,13 +482,13 @@ static int build_segments(const hexo_price_request* r, bool with_strikes,
     total += g.n_steps;
     const double D = exp(-kappa * h);                                   // HSimulation.tpp:58
     g.D = D;
-    g.c1 = eps * eps * D / kappa * (1 - D);                             // :60
-    g.c2 = theta * eps * eps / (2 * kappa) * (1. - D) * (1. - D);       // :60
+    g.m0 = theta * (1 - D);                                             // :59
+    g.c1h = 0.5 * (eps * eps * D / kappa * (1 - D));                    // :60 (halved)
+    g.c2h = 0.5 * (theta * eps * eps / (2 * kappa) * (1. - D) * (1. - D));
     g.K0 = -rho * kappa * theta / eps * h;                              // :75
     g.K1 = .5 * h * (kappa * rho / eps - .5) - rho / eps;               // :76
     g.K2 = .5 * h * (kappa * rho / eps - .5) + rho / eps;               // :77
-    g.K3 = .5 * h * (1 - rho * rho);                                    // :78
-    g.K4 = .5 * h * (1 - rho * rho);                                    // :79
+    g.K3 = .5 * h * (1 - rho * rho);                                    // :78 (= K4, :79)
     g.first_opt = with_strikes ? r->strike_offsets[k] : 0;
     g.n_strikes = with_strikes ? r->strike_offsets[k + 1] - r->strike_offsets[k] : 0;
     g.pad = 0;
@@ -466,15 +549,15 @@ static int plan_create(const hexo_price_request* r, uint64_t stream_begin, uint6
   const uint32_t n_opts = r->strike_offsets[r->n_chains];
   // block size: as many warps as the per-warp option accumulators allow
   int block = kMaxBlock;
-  while (block >= 32 && path_kernel_smem(block, n_opts) > g_ctx.smem_optin) block >>= 1;
+  while (block >= 32 && path_kernel_smem(block, n_opts, r->normal_mode) > g_ctx.smem_optin) block >>= 1;
   if (block < 32)
     return fail(HEXO_ERR_TOO_LARGE, "%u options need %zu B of shared memory per warp, limit %zu",
-                n_opts, path_kernel_smem(32, n_opts), g_ctx.smem_optin);
+                n_opts, path_kernel_smem(32, n_opts, r->normal_mode), g_ctx.smem_optin);
   p->payoff = r->payoff;
   p->normal_mode = r->normal_mode;
   p->n_opts = n_opts;
   p->block = (uint32_t)block;
-  p->smem = (uint32_t)path_kernel_smem(block, n_opts);
+  p->smem = (uint32_t)path_kernel_smem(block, n_opts, r->normal_mode);
   const uint64_t grid64 = (stream_count + block - 1) / block;
   if (grid64 > 0x7fffffffull) return fail(HEXO_ERR_TOO_LARGE, "too many streams for one launch");
   p->grid = (uint32_t)grid64;
@@ -496,7 +579,6 @@ static int plan_create(const hexo_price_request* r, uint64_t stream_begin, uint6
 
   PathArgs& a = p->args;
   a.v0 = r->p.v_0;
-  a.theta = r->p.v_m;
   a.S = r->S;
   a.lnS = log(r->S);  // HSimulation.tpp:90
   a.seed = r->seed;
@@ -802,11 +884,11 @@ int hexo_gpu_replay(const hexo_price_request* req, const double* tape, uint64_t 
   if (e == cudaSuccess) {
     const unsigned grid = (unsigned)((n_paths + 127) / 128);
     if (req->payoff == HEXO_PAYOFF_ASIAN)
-      qe_replay_kernel<HEXO_PAYOFF_ASIAN><<<grid, 128>>>(req->p.v_0, req->p.v_m, req->S, log(req->S),
+      qe_replay_kernel<HEXO_PAYOFF_ASIAN><<<grid, 128>>>(req->p.v_0, req->S, log(req->S),
                                                          req->n_chains, dseg, dtape, n_paths,
                                                          tape_steps, dfin);
     else
-      qe_replay_kernel<HEXO_PAYOFF_EUROPEAN><<<grid, 128>>>(req->p.v_0, req->p.v_m, req->S,
+      qe_replay_kernel<HEXO_PAYOFF_EUROPEAN><<<grid, 128>>>(req->p.v_0, req->S,
                                                             log(req->S), req->n_chains, dseg, dtape,
                                                             n_paths, tape_steps, dfin);
     e = cudaGetLastError();
