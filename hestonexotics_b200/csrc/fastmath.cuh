@@ -14,6 +14,27 @@
 
 namespace hexo {
 
+// Double-precision literals cannot be instruction immediates (unless their low
+// word is zero), and under register pressure ptxas re-materialises them with two
+// moves per use inside the step loop.  Living in the constant bank they become
+// free `c[3][..]` operands of DFMA/DADD.
+struct FmConst {
+  double inv720, inv120, inv24, inv6;  // Taylor coefficients of e^r
+  double invL;                         // 32/ln2
+  double nLhi, nLlo;                   // -(ln2/32) split in two
+  double magic;                        // 1.5 * 2^52
+  double tiny;                         // 1e-300: keeps sqrt arguments off exact zero
+  double u_max;                        // largest double below 1
+};
+__constant__ FmConst kFm = {
+    1.0 / 720.0, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0,
+    46.166241308446828384,
+    -2.16608493865351192653e-02, -5.96317165397058656257e-12,
+    6755399441055744.0,
+    1e-300,
+    0.99999999999999988898,
+};
+
 __device__ __forceinline__ double mufu_rcp64(double a) {
   double y;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
@@ -44,32 +65,24 @@ __device__ __forceinline__ double fast_sqrt(double a) {
   return fma(g, q * r, g);
 }
 
-// sqrt(a) for a >= 0 including exact zero (returns ~1e-150 instead of 0, which the
-// caller multiplies by a normal draw and adds to a log-spot of order 1).
-__device__ __forceinline__ double fast_sqrt_nonneg(double a) {
-  return fast_sqrt(fmax(a, 1e-300));
-}
-
 // exp(x) for |x| < 700: x = (32 k + j) ln2/32 + r, exp(x) = 2^k 2^(j/32) e^r with
 // |r| <= ln2/64 and a degree-6 Taylor polynomial (remainder r^7/5040 < 4e-18).
-// `tab` holds 2^(j/32), j = 0..31 (shared memory, filled by exp_table_init).
-__device__ __forceinline__ double fast_exp(double x, const double* __restrict__ tab) {
-  const double kMagic = 6755399441055744.0;          // 1.5 * 2^52
-  const double kInvL = 46.166241308446828384;        // 32/ln2
-  const double kLhi = 2.16608493865351192653e-02;    // ln2/32, high part (low bits zero)
-  const double kLlo = 5.96317165397058656257e-12;    // ln2/32 - kLhi
-  const double t = fma(x, kInvL, kMagic);
+// `tab_saddr` is the shared-space byte address of the 32-entry table 2^(j/32)
+// (filled by exp_table_init).
+__device__ __forceinline__ double fast_exp(double x, uint32_t tab_saddr) {
+  const double t = fma(x, kFm.invL, kFm.magic);
   const int n = __double2loint(t);                   // round-to-nearest integer of x*32/ln2
-  const double nd = t - kMagic;
-  double r = fma(nd, -kLhi, x);
-  r = fma(nd, -kLlo, r);
-  double p = fma(r, 1.0 / 720.0, 1.0 / 120.0);
-  p = fma(p, r, 1.0 / 24.0);
-  p = fma(p, r, 1.0 / 6.0);
+  const double nd = t - kFm.magic;
+  double r = fma(nd, kFm.nLhi, x);
+  r = fma(nd, kFm.nLlo, r);
+  double p = fma(r, kFm.inv720, kFm.inv120);
+  p = fma(p, r, kFm.inv24);
+  p = fma(p, r, kFm.inv6);
   p = fma(p, r, 0.5);
   p = fma(p, r, 1.0);
   p = p * r;                                         // e^r - 1
-  const double T = tab[n & 31];
+  double T;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(T) : "r"(tab_saddr + ((n & 31) << 3)));
   const double v = fma(T, p, T);
   // scale by 2^k: add k to the exponent field (v is in [1,2), k in [-1010,1010])
   const int k = n >> 5;

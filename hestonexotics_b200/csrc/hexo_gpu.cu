@@ -31,9 +31,7 @@
 #include <vector>
 
 #include "../../include/hexo_gpu.h"
-#include "normals.cuh"
-#include "qe.cuh"
-#include "shishua.cuh"
+#include "path_kernel.cuh"
 
 namespace hexo {
 
@@ -89,220 +87,6 @@ static int ensure_context() {
   return HEXO_OK;
 }
 
-// ---------------------------------------------------------------------------
-// K1: fused path kernel
-// ---------------------------------------------------------------------------
-constexpr int kMaxBlock = 256;
-constexpr int kStepsPerRound = 8;  // one shishua round = 16 words = 8 steps
-
-struct PathArgs {
-  double v0, S, lnS;
-  uint64_t seed;
-  uint64_t stream_begin;  // first global stream id of this launch
-  uint64_t stream_count;  // streams in this launch (one per thread)
-  uint64_t base_paths;    // every stream runs base_paths paths ...
-  uint64_t rem_streams;   // ... and global streams < rem_streams one more
-  uint32_t n_seg, n_opts;
-  const SegConst* segs;
-  const double* strikes;
-  double* partials;  // [gridDim.x][2*n_opts]
-};
-
-// Shared memory of the path kernel (per block):
-//   zring  [8][T] pairs (Z_V, Z_X) of the current generator round, float2 (F32
-//                 mode) or double2 (F64 mode);   T = threads per block
-//   uring  [8][T] raw variance words of the round (the uniform of the psi >= 1.5
-//                 branch comes from the same word as the normal it replaces)
-//   exptab [32]   2^(j/32)
-//   fvbuf  [W][32] final values of a warp at a maturity;  W = warps per block
-//   acc    [W][2][n_opts] lane-owned payoff sums / sums of squares
-__host__ __device__ inline size_t path_kernel_smem(int block, uint32_t n_opts, int normal_mode) {
-  const int warps = block / 32;
-  const size_t zbytes = (normal_mode == HEXO_NORMAL_F64 ? 16 : 8) * (size_t)kStepsPerRound * block;
-  return zbytes + (size_t)8 * kStepsPerRound * block + 32 * 8 + (size_t)32 * 8 * warps +
-         (size_t)warps * 2 * n_opts * 8;
-}
-
-template <int NORMAL_MODE>
-struct ZRing;
-
-// F32 mode: both normals of a step in one 8-byte word
-template <>
-struct ZRing<HEXO_NORMAL_F32> {
-  float2* z;  // this thread's column, stride T
-  int T;
-  static constexpr int kBytesPerStep = 8;
-  __device__ __forceinline__ void fill(const uint64_t (&o)[16]) {
-#pragma unroll
-    for (int s = 0; s < kStepsPerRound; ++s) {
-      float zv, zx;
-      normal2_f32(o[2 * s], o[2 * s + 1], zv, zx);
-      z[s * T] = make_float2(zv, zx);
-    }
-  }
-  __device__ __forceinline__ void get(int s, double& zv, double& zx) const {
-    const float2 v = z[s * T];
-    zv = (double)v.x;
-    zx = (double)v.y;
-  }
-};
-
-// F64 mode: central region for every draw, then a per-lane loop over the tails
-template <>
-struct ZRing<HEXO_NORMAL_F64> {
-  double2* z;
-  int T;
-  static constexpr int kBytesPerStep = 16;
-  __device__ __forceinline__ void fill(const uint64_t (&o)[16]) {
-    uint32_t tails = 0;
-#pragma unroll
-    for (int s = 0; s < kStepsPerRound; ++s) {
-      bool t0, t1;
-      const double zv = normal_central_f64(o[2 * s], t0);
-      const double zx = normal_central_f64(o[2 * s + 1], t1);
-      // a tail draw parks its raw word in the slot until the loop below replaces it
-      z[s * T] = make_double2(t0 ? __longlong_as_double((long long)o[2 * s]) : zv,
-                              t1 ? __longlong_as_double((long long)o[2 * s + 1]) : zx);
-      tails |= (t0 ? 1u : 0u) << (2 * s) | (t1 ? 1u : 0u) << (2 * s + 1);
-    }
-    double* zz = reinterpret_cast<double*>(z);
-    while (tails) {
-      const int j = __ffs(tails) - 1;
-      tails &= tails - 1;
-      double* slot = zz + (size_t)(j >> 1) * T * 2 + (j & 1);
-      *slot = normal_tail_f64((uint64_t)__double_as_longlong(*slot));
-    }
-  }
-  __device__ __forceinline__ void get(int s, double& zv, double& zx) const {
-    const double2 v = z[s * T];
-    zv = v.x;
-    zx = v.y;
-  }
-};
-
-template <int PAYOFF, int NORMAL_MODE>
-__global__ void __launch_bounds__(kMaxBlock, 2) heston_qe_paths_kernel(const PathArgs a) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int T = blockDim.x, nwarps = T >> 5;
-  using Ring = ZRing<NORMAL_MODE>;
-  unsigned char* sp = smem_raw;
-  Ring ring;
-  ring.z = reinterpret_cast<decltype(ring.z)>(sp) + tid;
-  ring.T = T;
-  sp += (size_t)Ring::kBytesPerStep * kStepsPerRound * T;
-  uint64_t* ucol = reinterpret_cast<uint64_t*>(sp) + tid;  // raw variance words, stride T
-  sp += (size_t)8 * kStepsPerRound * T;
-  double* exptab = reinterpret_cast<double*>(sp);
-  sp += 32 * 8;
-  double* fvbuf = reinterpret_cast<double*>(sp) + 32 * warp;
-  sp += (size_t)32 * 8 * nwarps;
-  double* acc_all = reinterpret_cast<double*>(sp);
-  double* my_sum = acc_all + (size_t)warp * 2 * a.n_opts;  // lane-owned slots
-  double* my_sq = my_sum + a.n_opts;
-  for (uint32_t j = lane; j < 2 * a.n_opts; j += 32) my_sum[j] = 0.0;
-  exp_table_init(exptab, tid, T);
-
-  const uint64_t slot = (uint64_t)blockIdx.x * T + tid;
-  const uint64_t sid = a.stream_begin + slot;
-  const uint64_t my_paths =
-      slot < a.stream_count ? a.base_paths + (sid < a.rem_streams ? 1u : 0u) : 0u;
-  // path counts are non-increasing in the stream id, so lane 0 holds the warp's maximum
-  const uint64_t warp_paths = __shfl_sync(0xffffffffu, my_paths, 0);
-
-  Shishua rng;
-  {
-    uint64_t o[16];
-    rng.init(a.seed, sid, 0, 0, o);
-#pragma unroll
-    for (int s = 0; s < kStepsPerRound; ++s) ucol[s * T] = o[2 * s];
-    ring.fill(o);
-  }
-  int pos = 0;  // next unread step of the round
-  __syncthreads();  // exptab
-
-  for (uint64_t p = 0; p < warp_paths; ++p) {
-    const bool active = p < my_paths;
-    // HQEAnderson::operator=(initial_state), HSimulation.tpp:26,87-94
-    double V = a.v0, lnX = a.lnS, X = a.S, Xprev = a.S;
-    double integral = 0.0;  // AAsianCallNonAdaptive::accumulated_value, reset per path (:34)
-    for (uint32_t k = 0; k < a.n_seg; ++k) {
-      const SegConst g = a.segs[k];
-      if (active) {
-        const uint32_t n = g.n_steps;
-        if (PAYOFF == HEXO_PAYOFF_ASIAN && k > 0 && n > 0) {
-          // The trapezoid of the step that crossed the previous expiry is added
-          // AFTER update_earliest switched the step size (HSimulation.tpp:42-44),
-          // i.e. with this segment's h.
-          integral += g.h * 0.5 * (X + Xprev);
-        }
-        const double Xa = X;
-        double sumX = 0.0;
-        for (uint32_t i = 0; i < n; ++i) {
-          if (pos == kStepsPerRound) {
-            uint64_t o[16];
-            rng.round(o);
-#pragma unroll
-            for (int s = 0; s < kStepsPerRound; ++s) ucol[s * T] = o[2 * s];
-            ring.fill(o);
-            pos = 0;
-          }
-          double zv, zx;
-          ring.get(pos, zv, zx);
-          const uint64_t* uword = ucol + pos * T;
-          ++pos;
-          qe_step(g, V, lnX, zv, [uword]() { return u64_to_unit(*uword); }, zx);
-          if (PAYOFF == HEXO_PAYOFF_ASIAN) {
-            Xprev = X;
-            X = fast_exp(lnX, exptab);       // HSimulation.tpp:81-82
-            if (i + 1 < n) sumX += X;        // all but the crossing step
-          } else if (i + 2 >= n) {           // European: X is only read at the expiry
-            Xprev = X;
-            X = fast_exp(lnX, exptab);
-          }
-        }
-        if (PAYOFF == HEXO_PAYOFF_ASIAN && n > 0) {
-          // sum over the first n-1 steps of h/2 (X_j + X_{j-1}), AsianContract.h:25-28
-          integral += g.h * 0.5 * (Xa - Xprev + 2.0 * sumX);
-        }
-      }
-      // accumulate_final_value, AsianContract.h:29-34 / VanillaContract.h:28-31
-      const double dx = X - Xprev;
-      const double fv = PAYOFF == HEXO_PAYOFF_ASIAN ? (integral + dx * g.w) / g.expiry
-                                                    : Xprev + dx * g.w;
-      __syncwarp();
-      fvbuf[lane] = fv;
-      const unsigned amask = __ballot_sync(0xffffffffu, active);
-      __syncwarp();
-      // final_payoff for every strike of this chain (HSimulation.tpp:39-40): lane
-      // l owns strikes l, l+32, ... and walks the warp's 32 final values.
-      for (uint32_t j = lane; j < g.n_strikes; j += 32) {
-        const double K = __ldg(a.strikes + g.first_opt + j);
-        double s = 0.0, q = 0.0;
-#pragma unroll 8
-        for (int l = 0; l < 32; ++l) {
-          if ((amask >> l) & 1u) {
-            const double pf = fmax(fvbuf[l] - K, 0.0);
-            s += pf;
-            q = fma(pf, pf, q);
-          }
-        }
-        my_sum[g.first_opt + j] += s;
-        my_sq[g.first_opt + j] += q;
-      }
-    }
-  }
-
-  // warps -> block partial, fixed order
-  __syncthreads();
-  const uint32_t n2 = 2 * a.n_opts;
-  for (uint32_t j = tid; j < n2; j += T) {
-    double s = 0.0;
-    for (int w = 0; w < nwarps; ++w) s += acc_all[(size_t)w * n2 + j];
-    a.partials[(size_t)blockIdx.x * n2 + j] = s;
-  }
-}
-
 // blocks -> sums, fixed order
 __global__ void reduce_partials_kernel(const double* __restrict__ partials, uint32_t n_blocks,
                                        uint32_t n2, double* __restrict__ out) {
@@ -352,9 +136,10 @@ template <int PAYOFF>
 __global__ void qe_replay_kernel(double v0, double S, double lnS, uint32_t n_seg,
                                  const SegConst* segs, const double* tape, uint64_t n_paths,
                                  uint32_t tape_steps, double* finals) {
-  __shared__ double exptab[32];
-  exp_table_init(exptab, threadIdx.x, blockDim.x);
+  __shared__ double exptab_mem[32];
+  exp_table_init(exptab_mem, threadIdx.x, blockDim.x);
   __syncthreads();
+  const uint32_t exptab = smem_addr(exptab_mem);
   const uint64_t path = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (path >= n_paths) return;
   const double* t = tape + (size_t)path * tape_steps * 3;

@@ -74,15 +74,10 @@ __device__ __forceinline__ float mufu_rcp(float x) {
   return y;
 }
 
-// per-draw scalar preparation: q = p - 1/2, and t = -ln(min(p, 1-p)) (>= 0)
-__device__ __forceinline__ void prep_f32(uint64_t w, float& q, float& t) {
-  const uint32_t hi = (uint32_t)(w >> 32), lo = (uint32_t)w;
-  q = (float)(int32_t)(hi ^ 0x80000000u) * 2.3283064365386963e-10f;  // 2^-32
-  const uint32_t flip = (uint32_t)((int32_t)hi >> 31);               // all ones when p >= 1/2
-  // v = p (q < 0) or ~p ~ 1 - p (q >= 0) as a 64-bit fraction; vf = v * 2^-32
-  const float vf = fmaf((float)(lo ^ flip), 2.3283064365386963e-10f, (float)(hi ^ flip));
-  // -ln(v 2^-64) = (32 - lg2(vf)) ln2
-  t = fmaf(mufu_lg2(vf), -0.69314718055994530942f, 22.180709777918249f);
+__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
 }
 
 // far tail of as241.f90:110-114 (r > 5, i.e. p < 1.4e-11) and the p in {0,1} case
@@ -102,9 +97,26 @@ __device__ __noinline__ float ppnd_far_tail_f32(float q, float t) {
 // Two draws -> two normals, single precision (as-built AS241)
 __device__ __forceinline__ void normal2_f32(uint64_t w0, uint64_t w1, float& z0, float& z1) {
   using P = Ppnd;
-  float q0, q1, t0, t1;
-  prep_f32(w0, q0, t0);
-  prep_f32(w1, q1, t1);
+  const uint32_t hi0 = (uint32_t)(w0 >> 32), lo0 = (uint32_t)w0;
+  const uint32_t hi1 = (uint32_t)(w1 >> 32), lo1 = (uint32_t)w1;
+  // q = p - 1/2 from the high word
+  const uint64_t q2 = fmul2(pack2((float)(int32_t)(hi0 ^ 0x80000000u),
+                                  (float)(int32_t)(hi1 ^ 0x80000000u)),
+                            HEXO_BC(2.3283064365386963e-10f));  // 2^-32
+  float q0, q1;
+  unpack2(q2, q0, q1);
+  // v = p (q < 0) or ~p ~ 1 - p (q >= 0) as a 64-bit fraction; vf = v 2^-32
+  const uint32_t f0 = (uint32_t)((int32_t)hi0 >> 31), f1 = (uint32_t)((int32_t)hi1 >> 31);
+  const uint64_t vf2 = ffma2(pack2((float)(lo0 ^ f0), (float)(lo1 ^ f1)),
+                             HEXO_BC(2.3283064365386963e-10f),
+                             pack2((float)(hi0 ^ f0), (float)(hi1 ^ f1)));
+  float vf0, vf1;
+  unpack2(vf2, vf0, vf1);
+  // t = -ln(v 2^-64) = (32 - lg2(vf)) ln2  >= 0
+  const uint64_t t2 = ffma2(pack2(mufu_lg2(vf0), mufu_lg2(vf1)), HEXO_BC(-0.69314718055994530942f),
+                            HEXO_BC(22.180709777918249f));
+  float t0, t1;
+  unpack2(t2, t0, t1);
   const float r0 = mufu_sqrt(t0), r1 = mufu_sqrt(t1);
   // central: q A(rc)/B(rc), rc = 0.180625 - q^2     (as241.f90:88-92)
   const uint64_t rc = pack2(fmaf(-q0, q0, (float)P::CONST1), fmaf(-q1, q1, (float)P::CONST1));
@@ -112,9 +124,9 @@ __device__ __forceinline__ void normal2_f32(uint64_t w0, uint64_t w1, float& z0,
                             (float)P::A3, (float)P::A2, (float)P::A1, (float)P::A0);
   const uint64_t denc = horner8x2(rc, (float)P::B7, (float)P::B6, (float)P::B5, (float)P::B4,
                                   (float)P::B3, (float)P::B2, (float)P::B1, 1.0f);
-  numc = fmul2(numc, pack2(q0, q1));
+  numc = fmul2(numc, q2);
   // intermediate tail: C(r-1.6)/D(r-1.6)             (as241.f90:104-109)
-  const uint64_t rm = pack2(r0 - (float)P::CONST2, r1 - (float)P::CONST2);
+  const uint64_t rm = fadd2(pack2(r0, r1), HEXO_BC(-(float)P::CONST2));
   const uint64_t numm = horner8x2(rm, (float)P::C7, (float)P::C6, (float)P::C5, (float)P::C4,
                                   (float)P::C3, (float)P::C2, (float)P::C1, (float)P::C0);
   const uint64_t denm = horner8x2(rm, (float)P::D7, (float)P::D6, (float)P::D5, (float)P::D4,
@@ -128,11 +140,12 @@ __device__ __forceinline__ void normal2_f32(uint64_t w0, uint64_t w1, float& z0,
   nm0 = __uint_as_float(__float_as_uint(nm0) ^ (__float_as_uint(q0) & 0x80000000u));
   nm1 = __uint_as_float(__float_as_uint(nm1) ^ (__float_as_uint(q1) & 0x80000000u));
   const bool c0 = fabsf(q0) <= (float)P::SPLIT1, c1 = fabsf(q1) <= (float)P::SPLIT1;
-  z0 = (c0 ? nc0 : nm0) * mufu_rcp(c0 ? dc0 : dm0);
-  z1 = (c1 ? nc1 : nm1) * mufu_rcp(c1 ? dc1 : dm1);
-  if (fmaxf(r0, r1) > (float)P::SPLIT2) {  // p < 1.4e-11: essentially never
-    if (r0 > (float)P::SPLIT2) z0 = ppnd_far_tail_f32(q0, t0);
-    if (r1 > (float)P::SPLIT2) z1 = ppnd_far_tail_f32(q1, t1);
+  const uint64_t z2 = fmul2(pack2(c0 ? nc0 : nm0, c1 ? nc1 : nm1),
+                            pack2(mufu_rcp(c0 ? dc0 : dm0), mufu_rcp(c1 ? dc1 : dm1)));
+  unpack2(z2, z0, z1);
+  if (fmaxf(t0, t1) > 25.0f) {  // r > 5, i.e. p < 1.4e-11: essentially never
+    if (t0 > 25.0f) z0 = ppnd_far_tail_f32(q0, t0);
+    if (t1 > 25.0f) z1 = ppnd_far_tail_f32(q1, t1);
   }
 }
 

@@ -1,0 +1,281 @@
+// hestonexotics_b200/csrc/path_kernel.cuh
+//
+// K1: the fused path kernel.  Replaces the reference's HSimulation::price<Scheme>
+// (src/HSimulation.tpp:10-51) and everything it calls per draw: the shishua
+// wrapper (src/RNG.cpp), PPND16 (src/as241.f90), the QE stepper
+// (HSimulation.tpp:52-86) and the payoff policies (src/inc/AsianContract.h,
+// src/inc/VanillaContract.h).
+//
+//  * one thread = one independent shishua stream (seed {seed, stream, 0, 0});
+//    RNG state, variance, log-spot and the running integral stay in registers;
+//    no path data touches HBM;
+//  * every 8 steps a thread advances its generator one round (16 words), turns
+//    them into 8 (Z_V, Z_X) pairs in one batch (normals.cuh) and parks them in
+//    its own column of shared memory; the step loop reads one pair per step;
+//  * when a maturity is reached the 32 final values of a warp are exchanged
+//    through shared memory and each lane owns a strided subset of the strikes,
+//    so per-option sums are accumulated without atomics and in a fixed order;
+//  * warps -> block partials (shared memory), blocks -> sums (second tiny
+//    kernel), both in fixed order: results are reproducible for a given launch
+//    geometry.
+#pragma once
+#include <stdint.h>
+
+#include <type_traits>
+
+#include "../../include/hexo_gpu.h"
+#include "normals.cuh"
+#include "qe.cuh"
+#include "shishua.cuh"
+
+namespace hexo {
+
+constexpr int kMaxBlock = 256;
+constexpr int kStepsPerRound = 8;  // one shishua round = 16 words = 8 steps
+
+struct PathArgs {
+  double v0, S, lnS;
+  uint64_t seed;
+  uint64_t stream_begin;  // first global stream id of this launch
+  uint64_t stream_count;  // streams in this launch (one per thread)
+  uint64_t base_paths;    // every stream runs base_paths paths ...
+  uint64_t rem_streams;   // ... and global streams < rem_streams one more
+  uint32_t n_seg, n_opts;
+  const SegConst* segs;
+  const double* strikes;
+  double* partials;  // [gridDim.x][2*n_opts]
+};
+
+// Shared memory of the path kernel (per block), T = threads, W = warps:
+//   zring  [8][T] pairs (Z_V, Z_X) of the current generator round, float2 (F32
+//                 mode) or double2 (F64 mode)
+//   uring  [8][T] raw variance words of the round (the uniform of the psi >= 1.5
+//                 branch comes from the same word as the normal it replaces)
+//   exptab [32]   2^(j/32)
+//   fvbuf  [W][32] final values of a warp at a maturity
+//   acc    [W][2][n_opts] lane-owned payoff sums / sums of squares
+__host__ __device__ inline size_t path_kernel_smem(int block, uint32_t n_opts, int normal_mode) {
+  const int warps = block / 32;
+  const size_t zbytes = (normal_mode == HEXO_NORMAL_F64 ? 16 : 8) * (size_t)kStepsPerRound * block;
+  return zbytes + (size_t)8 * kStepsPerRound * block + 32 * 8 + (size_t)32 * 8 * warps +
+         (size_t)warps * 2 * n_opts * 8;
+}
+
+// ---- shared-space accessors (32-bit addresses: no generic-pointer arithmetic
+// in the step loop) -------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_addr(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void sts_b64(uint32_t addr, uint64_t v) {
+  asm volatile("st.shared.b64 [%0], %1;" ::"r"(addr), "l"(v));
+}
+__device__ __forceinline__ uint64_t lds_b64(uint32_t addr) {
+  uint64_t v;
+  asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts_f64x2(uint32_t addr, double a, double b) {
+  asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(a), "d"(b));
+}
+__device__ __forceinline__ void lds_f64x2(uint32_t addr, double& a, double& b) {
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "r"(addr));
+}
+__device__ __forceinline__ void sts_f64(uint32_t addr, double a) {
+  asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(a));
+}
+__device__ __forceinline__ double lds_f64(uint32_t addr) {
+  double a;
+  asm volatile("ld.shared.f64 %0, [%1];" : "=d"(a) : "r"(addr));
+  return a;
+}
+
+template <int NORMAL_MODE>
+struct ZRing;
+
+// F32 mode: both normals of a step in one 8-byte word
+template <>
+struct ZRing<HEXO_NORMAL_F32> {
+  static constexpr int kBytesPerStep = 8;
+  // zcol = shared address of this thread's slot for step 0, stride = T*8
+  static __device__ __forceinline__ void fill(const uint64_t (&o)[16], uint32_t zcol,
+                                              uint32_t stride) {
+#pragma unroll
+    for (int s = 0; s < kStepsPerRound; ++s) {
+      float zv, zx;
+      normal2_f32(o[2 * s], o[2 * s + 1], zv, zx);
+      sts_b64(zcol + s * stride, pack2(zv, zx));
+    }
+  }
+  static __device__ __forceinline__ void get(uint32_t addr, double& zv, double& zx) {
+    float a, b;
+    unpack2(lds_b64(addr), a, b);
+    zv = (double)a;
+    zx = (double)b;
+  }
+};
+
+// F64 mode: central region for every draw, then a per-lane loop over the tails
+template <>
+struct ZRing<HEXO_NORMAL_F64> {
+  static constexpr int kBytesPerStep = 16;
+  static __device__ __forceinline__ void fill(const uint64_t (&o)[16], uint32_t zcol,
+                                              uint32_t stride) {
+    uint32_t tails = 0;
+#pragma unroll
+    for (int s = 0; s < kStepsPerRound; ++s) {
+      bool t0, t1;
+      const double zv = normal_central_f64(o[2 * s], t0);
+      const double zx = normal_central_f64(o[2 * s + 1], t1);
+      // a tail draw parks its raw word in the slot until the loop below replaces it
+      sts_f64x2(zcol + s * stride, t0 ? __longlong_as_double((long long)o[2 * s]) : zv,
+                t1 ? __longlong_as_double((long long)o[2 * s + 1]) : zx);
+      tails |= (t0 ? 1u : 0u) << (2 * s) | (t1 ? 1u : 0u) << (2 * s + 1);
+    }
+    while (tails) {
+      const int j = __ffs(tails) - 1;
+      tails &= tails - 1;
+      const uint32_t slot = zcol + (j >> 1) * stride + (j & 1) * 8;
+      sts_f64(slot, normal_tail_f64((uint64_t)__double_as_longlong(lds_f64(slot))));
+    }
+  }
+  static __device__ __forceinline__ void get(uint32_t addr, double& zv, double& zx) {
+    lds_f64x2(addr, zv, zx);
+  }
+};
+
+template <int PAYOFF, int NORMAL_MODE>
+__global__ void __launch_bounds__(kMaxBlock, 2) heston_qe_paths_kernel(const PathArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int T = blockDim.x, nwarps = T >> 5;
+  using Ring = ZRing<NORMAL_MODE>;
+  constexpr bool kAsian = PAYOFF == HEXO_PAYOFF_ASIAN;
+
+  unsigned char* sp = smem_raw;
+  const uint32_t zstride = Ring::kBytesPerStep * T, ustride = 8 * T;
+  const uint32_t zcol = smem_addr(sp) + Ring::kBytesPerStep * tid;
+  sp += (size_t)Ring::kBytesPerStep * kStepsPerRound * T;
+  const uint32_t ucol = smem_addr(sp) + 8 * tid;  // raw variance words
+  sp += (size_t)8 * kStepsPerRound * T;
+  double* exptab = reinterpret_cast<double*>(sp);
+  const uint32_t exptab_s = smem_addr(sp);
+  sp += 32 * 8;
+  double* fvbuf = reinterpret_cast<double*>(sp) + 32 * warp;
+  sp += (size_t)32 * 8 * nwarps;
+  double* acc_all = reinterpret_cast<double*>(sp);
+  double* my_sum = acc_all + (size_t)warp * 2 * a.n_opts;  // lane-owned slots
+  double* my_sq = my_sum + a.n_opts;
+  for (uint32_t j = lane; j < 2 * a.n_opts; j += 32) my_sum[j] = 0.0;
+  exp_table_init(exptab, tid, T);
+
+  const uint64_t slot = (uint64_t)blockIdx.x * T + tid;
+  const uint64_t sid = a.stream_begin + slot;
+  const uint64_t my_paths =
+      slot < a.stream_count ? a.base_paths + (sid < a.rem_streams ? 1u : 0u) : 0u;
+  // path counts are non-increasing in the stream id, so lane 0 holds the warp's maximum
+  const uint64_t warp_paths = __shfl_sync(0xffffffffu, my_paths, 0);
+
+  Shishua rng;
+  auto refill = [&](uint64_t (&o)[16]) {
+#pragma unroll
+    for (int s = 0; s < kStepsPerRound; ++s) sts_b64(ucol + s * ustride, o[2 * s]);
+    Ring::fill(o, zcol, zstride);
+  };
+  {
+    uint64_t o[16];
+    rng.init(a.seed, sid, 0, 0, o);
+    refill(o);
+  }
+  uint32_t pos = 0;  // next unread step of the round
+  __syncthreads();   // exptab
+
+  for (uint64_t p = 0; p < warp_paths; ++p) {
+    const bool active = p < my_paths;
+    // HQEAnderson::operator=(initial_state), HSimulation.tpp:26,87-94
+    double V = a.v0, lnX = a.lnS, X = a.S, Xprev = a.S;
+    double integral = 0.0;  // AAsianCallNonAdaptive::accumulated_value, reset per path (:34)
+    for (uint32_t k = 0; k < a.n_seg; ++k) {
+      const SegConst g = a.segs[k];
+      if (active) {
+        const uint32_t n = g.n_steps;
+        if (kAsian && k > 0 && n > 0) {
+          // The trapezoid of the step that crossed the previous expiry is added
+          // AFTER update_earliest switched the step size (HSimulation.tpp:42-44),
+          // i.e. with this segment's h.
+          integral += g.h * 0.5 * (X + Xprev);
+        }
+        const double Xa = X;
+        double sumX = 0.0;
+        // `count` steps of this segment; WITH_X: also X = exp(ln X) (HSimulation.tpp:81-82)
+        auto run = [&](uint32_t count, auto with_x) {
+          while (count) {
+            if (pos == kStepsPerRound) {
+              uint64_t o[16];
+              rng.round(o);
+              refill(o);
+              pos = 0;
+            }
+            uint32_t m = min(kStepsPerRound - pos, count);
+            count -= m;
+            uint32_t za = zcol + pos * zstride, ua = ucol + pos * ustride;
+            pos += m;
+            for (; m; --m, za += zstride, ua += ustride) {
+              double zv, zx;
+              Ring::get(za, zv, zx);
+              qe_step(g, V, lnX, zv, [ua]() { return u64_to_unit(lds_b64(ua)); }, zx);
+              if (decltype(with_x)::value) {
+                Xprev = X;
+                X = fast_exp(lnX, exptab_s);
+                if (kAsian) sumX += X;
+              }
+            }
+          }
+        };
+        if (kAsian) {
+          run(n, std::true_type{});
+          // trapezoids of all but the crossing step: h/2 sum_{j<n} (X_j + X_{j-1}),
+          // AsianContract.h:25-28; sumX includes the crossing step's X, take it out
+          if (n > 0) integral += g.h * 0.5 * (Xa - Xprev + 2.0 * (sumX - X));
+        } else {
+          // European: X is only read at the expiry, so only the last two steps need it
+          if (n > 2) run(n - 2, std::false_type{});
+          run(min(n, 2u), std::true_type{});
+        }
+      }
+      // accumulate_final_value, AsianContract.h:29-34 / VanillaContract.h:28-31
+      const double dx = X - Xprev;
+      const double fv = kAsian ? (integral + dx * g.w) / g.expiry : Xprev + dx * g.w;
+      __syncwarp();
+      fvbuf[lane] = fv;
+      const unsigned amask = __ballot_sync(0xffffffffu, active);
+      __syncwarp();
+      // final_payoff for every strike of this chain (HSimulation.tpp:39-40): lane
+      // l owns strikes l, l+32, ... and walks the warp's 32 final values.
+      for (uint32_t j = lane; j < g.n_strikes; j += 32) {
+        const double K = __ldg(a.strikes + g.first_opt + j);
+        double s = 0.0, q = 0.0;
+#pragma unroll 8
+        for (int l = 0; l < 32; ++l) {
+          if ((amask >> l) & 1u) {
+            const double pf = fmax(fvbuf[l] - K, 0.0);
+            s += pf;
+            q = fma(pf, pf, q);
+          }
+        }
+        my_sum[g.first_opt + j] += s;
+        my_sq[g.first_opt + j] += q;
+      }
+    }
+  }
+
+  // warps -> block partial, fixed order
+  __syncthreads();
+  const uint32_t n2 = 2 * a.n_opts;
+  for (uint32_t j = tid; j < n2; j += T) {
+    double s = 0.0;
+    for (int w = 0; w < nwarps; ++w) s += acc_all[(size_t)w * n2 + j];
+    a.partials[(size_t)blockIdx.x * n2 + j] = s;
+  }
+}
+
+}  // namespace hexo

@@ -51,7 +51,7 @@ __device__ __forceinline__ void qe_step(const SegConst& g, double& V, double& ln
   if (psih < 0.75) {                                        // :63  psi < 1.5
     const double c = fast_sqrt(1.0 - psih);
     const double d = 1.0 - c;
-    const double e = fast_sqrt_nonneg(c * d);
+    const double e = fast_sqrt(fma(c, d, kFm.tiny));  // c d >= 0; never exactly 0 for rsqrt
     Vn = m * fma(zv, fma(d, zv, e + e), c);                 // :64-68
   } else {
     const double psi = psih + psih;
@@ -59,11 +59,13 @@ __device__ __forceinline__ void qe_step(const SegConst& g, double& V, double& ln
     const double beta = 2.0 / (m * (psi + 1.0));            // :71
     // U = 1.0 (probability 2^-54) would make the reference take log(x/0) = inf;
     // clamp to the largest double below 1 instead.
-    const double u = fmin(uv(), 0.99999999999999988898);    // :72
+    const double u = fmin(uv(), kFm.u_max);                 // :72
     Vn = p < u ? log((1.0 - p) / (1.0 - u)) / beta : 0.0;   // :73
   }
   // :80 with K3 == K4
-  const double sq = fast_sqrt_nonneg(g.K3 * (V + Vn));
+  // V + V' can be exactly 0 (both steps in the zero-mass branch); the 1e-300 keeps the
+  // rsqrt seed finite and changes nothing otherwise
+  const double sq = fast_sqrt(fma(g.K3, V + Vn, kFm.tiny));
   lnX = fma(sq, zx, fma(g.K2, Vn, fma(g.K1, V, lnX + g.K0)));
   V = Vn;
 }
