@@ -25,6 +25,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -304,8 +305,9 @@ static PathKernel pick_kernel(int payoff, int normal_mode) {
 }
 
 static uint64_t default_streams(uint64_t n_paths, int n_gpus) {
-  // one wave of resident threads per GPU: 2 blocks x 256 threads per SM
-  const uint64_t per_gpu = (uint64_t)(g_ctx.ready ? g_ctx.sm_count : 148) * 2 * kMaxBlock;
+  // one wave of resident threads per GPU
+  const uint64_t per_gpu =
+      (uint64_t)(g_ctx.ready ? g_ctx.sm_count : 148) * kMinBlocksPerSM * kMaxBlock;
   uint64_t s = per_gpu * (uint64_t)std::max(n_gpus, 1);
   if (s > n_paths) s = n_paths;
   return std::max<uint64_t>(s, 1);
@@ -334,6 +336,10 @@ static int plan_create(const hexo_price_request* r, uint64_t stream_begin, uint6
   const uint32_t n_opts = r->strike_offsets[r->n_chains];
   // block size: as many warps as the per-warp option accumulators allow
   int block = kMaxBlock;
+  if (const char* e = getenv("HEXO_BLOCK")) {  // development knob: 32..256, multiple of 32
+    const int b = atoi(e);
+    if (b >= 32 && b <= kMaxBlock && b % 32 == 0) block = b;
+  }
   while (block >= 32 && path_kernel_smem(block, n_opts, r->normal_mode) > g_ctx.smem_optin) block >>= 1;
   if (block < 32)
     return fail(HEXO_ERR_TOO_LARGE, "%u options need %zu B of shared memory per warp, limit %zu",

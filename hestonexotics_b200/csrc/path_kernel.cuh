@@ -31,6 +31,10 @@
 namespace hexo {
 
 constexpr int kMaxBlock = 256;
+#ifndef HEXO_MIN_BLOCKS
+#define HEXO_MIN_BLOCKS 2
+#endif
+constexpr int kMinBlocksPerSM = HEXO_MIN_BLOCKS;  // register budget: 65536 / (256 * this)
 constexpr int kStepsPerRound = 8;  // one shishua round = 16 words = 8 steps
 
 struct PathArgs {
@@ -144,7 +148,7 @@ struct ZRing<HEXO_NORMAL_F64> {
 };
 
 template <int PAYOFF, int NORMAL_MODE>
-__global__ void __launch_bounds__(kMaxBlock, 2) heston_qe_paths_kernel(const PathArgs a) {
+__global__ void __launch_bounds__(kMaxBlock, kMinBlocksPerSM) heston_qe_paths_kernel(const PathArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int T = blockDim.x, nwarps = T >> 5;
@@ -206,8 +210,12 @@ __global__ void __launch_bounds__(kMaxBlock, 2) heston_qe_paths_kernel(const Pat
         }
         const double Xa = X;
         double sumX = 0.0;
-        // `count` steps of this segment; WITH_X: also X = exp(ln X) (HSimulation.tpp:81-82)
+        // `count` (> 0) steps of this segment, software-pipelined: iteration j does the
+        // log-spot / exp half of step j-1 next to the variance half of step j.
+        // with_x: also X = exp(ln X) (HSimulation.tpp:81-82)
         auto run = [&](uint32_t count, auto with_x) {
+          double Vold = V, zx_pend = 0.0;  // (V_{j-1}, Z_X of step j-1) of the pending half
+          bool first = true;
           while (count) {
             if (pos == kStepsPerRound) {
               uint64_t o[16];
@@ -219,27 +227,48 @@ __global__ void __launch_bounds__(kMaxBlock, 2) heston_qe_paths_kernel(const Pat
             count -= m;
             uint32_t za = zcol + pos * zstride, ua = ucol + pos * ustride;
             pos += m;
+            if (first) {  // prologue: variance half of the first step
+              first = false;
+              double zv;
+              Ring::get(za, zv, zx_pend);
+              Vold = V;
+              V = qe_variance(g, Vold, zv, [ua]() { return u64_to_unit(lds_b64(ua)); });
+              --m, za += zstride, ua += ustride;
+            }
             for (; m; --m, za += zstride, ua += ustride) {
               double zv, zx;
               Ring::get(za, zv, zx);
-              qe_step(g, V, lnX, zv, [ua]() { return u64_to_unit(lds_b64(ua)); }, zx);
+              // second half of the previous step
+              lnX = qe_logspot(g, lnX, Vold, V, zx_pend);
               if (decltype(with_x)::value) {
                 Xprev = X;
                 X = fast_exp(lnX, exptab_s);
                 if (kAsian) sumX += X;
               }
+              // first half of this step
+              const double Vn = qe_variance(g, V, zv, [ua]() { return u64_to_unit(lds_b64(ua)); });
+              Vold = V;
+              V = Vn;
+              zx_pend = zx;
             }
+          }
+          // epilogue: second half of the last step
+          lnX = qe_logspot(g, lnX, Vold, V, zx_pend);
+          if (decltype(with_x)::value) {
+            Xprev = X;
+            X = fast_exp(lnX, exptab_s);
+            if (kAsian) sumX += X;
           }
         };
         if (kAsian) {
-          run(n, std::true_type{});
+          if (n > 0) run(n, std::true_type{});
           // trapezoids of all but the crossing step: h/2 sum_{j<n} (X_j + X_{j-1}),
           // AsianContract.h:25-28; sumX includes the crossing step's X, take it out
           if (n > 0) integral += g.h * 0.5 * (Xa - Xprev + 2.0 * (sumX - X));
         } else {
           // European: X is only read at the expiry, so only the last two steps need it
           if (n > 2) run(n - 2, std::false_type{});
-          run(min(n, 2u), std::true_type{});
+          if (n > 0) run(min(n, 2u), std::true_type{});
         }
       }
       // accumulate_final_value, AsianContract.h:29-34 / VanillaContract.h:28-31

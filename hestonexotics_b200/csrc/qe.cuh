@@ -37,23 +37,26 @@ struct SegConst {
   uint32_t n_steps, first_opt, n_strikes, pad;
 };
 
-// (V, ln X) -> next step.  src/HSimulation.tpp:59-80.
+// The step is split in two halves so that the path kernel can software-pipeline
+// them: the variance recursion V -> V' is the only long loop-carried dependency;
+// the log-spot / exp half of step i hangs off (V_i, V_{i+1}) and can overlap the
+// variance half of step i+1.
+
+// Variance half, src/HSimulation.tpp:59-73.
 //   zv : variance normal (used when psi < 1.5)
 //   uv : callable returning the variance UNIFORM of the same draw (psi >= 1.5)
-//   zx : log-spot normal
 template <class UniformFn>
-__device__ __forceinline__ void qe_step(const SegConst& g, double& V, double& lnX,
-                                        const double zv, const UniformFn& uv, const double zx) {
+__device__ __forceinline__ double qe_variance(const SegConst& g, const double V, const double zv,
+                                              const UniformFn& uv) {
   const double m = fma(V, g.D, g.m0);                       // :59
   const double s2h = fabs(fma(V, g.c1h, g.c2h));            // :60  (s^2/2)
   const double psih = s2h * fast_rcp(m * m);                // :61  (psi/2)
-  double Vn;
-  if (psih < 0.75) {                                        // :63  psi < 1.5
-    const double c = fast_sqrt(1.0 - psih);
-    const double d = 1.0 - c;
-    const double e = fast_sqrt(fma(c, d, kFm.tiny));  // c d >= 0; never exactly 0 for rsqrt
-    Vn = m * fma(zv, fma(d, zv, e + e), c);                 // :64-68
-  } else {
+  // quadratic branch, evaluated unconditionally (NaN when psi/2 > 1, replaced below)
+  const double c = fast_sqrt(1.0 - psih);
+  const double d = 1.0 - c;
+  const double e = fast_sqrt(fma(c, d, kFm.tiny));          // c d >= 0; never exactly 0 for rsqrt
+  double Vn = m * fma(zv, fma(d, zv, e + e), c);            // :64-68
+  if (!(psih < 0.75)) {                                     // :63  psi >= 1.5 (rare)
     const double psi = psih + psih;
     const double p = (psi - 1.0) / (psi + 1.0);             // :70
     const double beta = 2.0 / (m * (psi + 1.0));            // :71
@@ -62,11 +65,24 @@ __device__ __forceinline__ void qe_step(const SegConst& g, double& V, double& ln
     const double u = fmin(uv(), kFm.u_max);                 // :72
     Vn = p < u ? log((1.0 - p) / (1.0 - u)) / beta : 0.0;   // :73
   }
-  // :80 with K3 == K4
+  return Vn;
+}
+
+// Log-spot half, src/HSimulation.tpp:75-80 with K3 == K4.
+__device__ __forceinline__ double qe_logspot(const SegConst& g, const double lnX, const double V,
+                                             const double Vn, const double zx) {
   // V + V' can be exactly 0 (both steps in the zero-mass branch); the 1e-300 keeps the
   // rsqrt seed finite and changes nothing otherwise
   const double sq = fast_sqrt(fma(g.K3, V + Vn, kFm.tiny));
-  lnX = fma(sq, zx, fma(g.K2, Vn, fma(g.K1, V, lnX + g.K0)));
+  return fma(sq, zx, fma(g.K2, Vn, fma(g.K1, V, lnX + g.K0)));
+}
+
+// (V, ln X) -> next step, both halves
+template <class UniformFn>
+__device__ __forceinline__ void qe_step(const SegConst& g, double& V, double& lnX,
+                                        const double zv, const UniformFn& uv, const double zx) {
+  const double Vn = qe_variance(g, V, zv, uv);
+  lnX = qe_logspot(g, lnX, V, Vn, zx);
   V = Vn;
 }
 
