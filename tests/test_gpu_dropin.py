@@ -1,0 +1,34 @@
+"""The drop-in from the reference's own language: oracle/_ref/hexo_dropin is compiled from the
+reference's unchanged C++ headers plus hestonexotics_b200/cpp/hexo_gpu_adapter.hpp and calls
+HSimulation::price<Scheme> (CPU, reference code) and HSimulation::price_gpu<Scheme> (C ABI -> CUDA)
+on the same synthetic option chain, like the PRICE case of src/Main.cpp:75-96."""
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "oracle", "_ref", "hexo_dropin")
+
+
+@pytest.mark.parametrize("kind", ["asian", "european"])
+def test_cpp_dropin_matches_reference_cpu(gpu, kind):
+    if not os.path.exists(BIN):
+        pytest.skip("oracle/_ref/hexo_dropin not built (needs the reference tree at build time)")
+    n_cpu, n_gpu = 20000, 2_000_000
+    out = subprocess.run([BIN, kind, str(n_cpu), str(n_gpu), "100"], capture_output=True, text=True,
+                         timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    res = json.loads(out.stdout)
+    ref, got, se = (np.array(res[k]) for k in ("reference", "gpu", "gpu_stderr"))
+    assert ref.shape == got.shape == (9,)
+    se_ref = se * np.sqrt(n_gpu / n_cpu)           # same payoff variance, fewer paths
+    z = (got - ref) / np.hypot(se, se_ref)
+    assert np.abs(z).max() < 3.5, z                # 9 options: 3.5 sigma ~ 0.4 % false alarm
+    # chain-major order: within each maturity prices fall with the strike (90, 100, 110)
+    g = got.reshape(3, 3)
+    assert (np.diff(g, axis=1) < 0).all() and (np.diff(g[:, 1]) > 0).all()
