@@ -293,15 +293,21 @@ struct Plan {
   uint64_t steps_per_path = 0, path_steps = 0, n_streams = 0;
   void* blob = nullptr;       // [segs | strikes | partials | sums]
   double* sums_dev = nullptr; // inside blob unless caller-supplied
+  size_t gacc_bytes = 0;
 };
 
 typedef void (*PathKernel)(const PathArgs);
-static PathKernel pick_kernel(int payoff, int normal_mode) {
+template <bool INL>
+static PathKernel pick_kernel_t(int payoff, int normal_mode) {
   if (payoff == HEXO_PAYOFF_ASIAN)
-    return normal_mode == HEXO_NORMAL_F64 ? heston_qe_paths_kernel<HEXO_PAYOFF_ASIAN, 1>
-                                          : heston_qe_paths_kernel<HEXO_PAYOFF_ASIAN, 0>;
-  return normal_mode == HEXO_NORMAL_F64 ? heston_qe_paths_kernel<HEXO_PAYOFF_EUROPEAN, 1>
-                                        : heston_qe_paths_kernel<HEXO_PAYOFF_EUROPEAN, 0>;
+    return normal_mode == HEXO_NORMAL_F64 ? heston_qe_paths_kernel<HEXO_PAYOFF_ASIAN, 1, INL>
+                                          : heston_qe_paths_kernel<HEXO_PAYOFF_ASIAN, 0, INL>;
+  return normal_mode == HEXO_NORMAL_F64 ? heston_qe_paths_kernel<HEXO_PAYOFF_EUROPEAN, 1, INL>
+                                        : heston_qe_paths_kernel<HEXO_PAYOFF_EUROPEAN, 0, INL>;
+}
+static PathKernel pick_kernel(int payoff, int normal_mode, uint32_t n_seg) {
+  return n_seg <= (uint32_t)kInlineSegs ? pick_kernel_t<true>(payoff, normal_mode)
+                                        : pick_kernel_t<false>(payoff, normal_mode);
 }
 
 static uint64_t default_streams(uint64_t n_paths, int n_gpus) {
@@ -334,21 +340,20 @@ static int plan_create(const hexo_price_request* r, uint64_t stream_begin, uint6
   rc = build_segments(r, true, segs, &p->steps_per_path);
   if (rc) return rc;
   const uint32_t n_opts = r->strike_offsets[r->n_chains];
-  // block size: as many warps as the per-warp option accumulators allow
+  // Per-warp option accumulators live in shared memory while that leaves room for
+  // kMinBlocksPerSM blocks per SM; larger chains accumulate in (L2-resident) device memory.
   int block = kMaxBlock;
   if (const char* e = getenv("HEXO_BLOCK")) {  // development knob: 32..256, multiple of 32
     const int b = atoi(e);
     if (b >= 32 && b <= kMaxBlock && b % 32 == 0) block = b;
   }
-  while (block >= 32 && path_kernel_smem(block, n_opts, r->normal_mode) > g_ctx.smem_optin) block >>= 1;
-  if (block < 32)
-    return fail(HEXO_ERR_TOO_LARGE, "%u options need %zu B of shared memory per warp, limit %zu",
-                n_opts, path_kernel_smem(32, n_opts, r->normal_mode), g_ctx.smem_optin);
+  const size_t smem_budget = std::min(g_ctx.smem_optin, (size_t)(227 * 1024) / kMinBlocksPerSM);
+  const bool acc_in_smem = path_kernel_smem(block, n_opts, r->normal_mode, true) <= smem_budget;
   p->payoff = r->payoff;
   p->normal_mode = r->normal_mode;
   p->n_opts = n_opts;
   p->block = (uint32_t)block;
-  p->smem = (uint32_t)path_kernel_smem(block, n_opts, r->normal_mode);
+  p->smem = (uint32_t)path_kernel_smem(block, n_opts, r->normal_mode, acc_in_smem);
   const uint64_t grid64 = (stream_count + block - 1) / block;
   if (grid64 > 0x7fffffffull) return fail(HEXO_ERR_TOO_LARGE, "too many streams for one launch");
   p->grid = (uint32_t)grid64;
@@ -359,9 +364,15 @@ static int plan_create(const hexo_price_request* r, uint64_t stream_begin, uint6
   const size_t strike_bytes = (size_t)n_opts * sizeof(double);
   const size_t part_bytes = (size_t)p->grid * 2 * n_opts * sizeof(double);
   const size_t sums_bytes = (size_t)2 * n_opts * sizeof(double);
+  const size_t gacc_bytes =
+      acc_in_smem ? 0 : (size_t)p->grid * (block / 32) * 2 * n_opts * sizeof(double);
+  if (gacc_bytes > ((size_t)8 << 30))
+    return fail(HEXO_ERR_TOO_LARGE, "%u options x %u blocks need %zu bytes of accumulators", n_opts,
+                p->grid, gacc_bytes);
   auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
   const size_t off_strikes = up(seg_bytes), off_part = off_strikes + up(strike_bytes),
-               off_sums = off_part + up(part_bytes), total = off_sums + up(sums_bytes);
+               off_sums = off_part + up(part_bytes), off_gacc = off_sums + up(sums_bytes),
+               total = off_gacc + up(gacc_bytes);
   HEXO_CUDA(cudaMallocAsync(&p->blob, total, st));
   unsigned char* base = static_cast<unsigned char*>(p->blob);
   HEXO_CUDA(cudaMemcpyAsync(base, segs.data(), seg_bytes, cudaMemcpyHostToDevice, st));
@@ -380,17 +391,21 @@ static int plan_create(const hexo_price_request* r, uint64_t stream_begin, uint6
   a.n_seg = r->n_chains;
   a.n_opts = n_opts;
   a.segs = reinterpret_cast<const SegConst*>(base);
+  for (size_t k = 0; k < segs.size() && k < (size_t)kInlineSegs; ++k) a.seg_inline[k] = segs[k];
   a.strikes = reinterpret_cast<const double*>(base + off_strikes);
   a.partials = reinterpret_cast<double*>(base + off_part);
+  a.gacc = acc_in_smem ? nullptr : reinterpret_cast<double*>(base + off_gacc);
+  p->gacc_bytes = gacc_bytes;
 
-  PathKernel kern = pick_kernel(p->payoff, p->normal_mode);
+  PathKernel kern = pick_kernel(p->payoff, p->normal_mode, p->args.n_seg);
   HEXO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem));
   return HEXO_OK;
 }
 
 // enqueue path kernel + reduction; sums land in `sums_out_dev` (or the plan's own buffer)
 static int plan_launch(const Plan* p, cudaStream_t st, double* sums_out_dev) {
-  PathKernel kern = pick_kernel(p->payoff, p->normal_mode);
+  PathKernel kern = pick_kernel(p->payoff, p->normal_mode, p->args.n_seg);
+  if (p->args.gacc) HEXO_CUDA(cudaMemsetAsync(p->args.gacc, 0, p->gacc_bytes, st));
   kern<<<p->grid, p->block, p->smem, st>>>(p->args);
   HEXO_CUDA(cudaGetLastError());
   const uint32_t n2 = 2 * p->n_opts;

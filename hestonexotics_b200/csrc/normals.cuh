@@ -4,18 +4,19 @@
 // standard normals, i.e. RNG::setup_u + RNG::setup_g of the reference
 // (src/RNG.cpp:28-43: u64 -> [0,1] -> ppnd16) without the 8 MiB buffers.
 //
-// F32 mode (the reference AS BUILT, as241.f90:20-25): two draws are evaluated
-// together in packed single precision (fma.rn.f32x2 -> FFMA2, Blackwell's
-// two-wide FP32 FMA), the AS241 coefficients appear as immediates, and the
-// central (|q| <= 0.425) and intermediate-tail (r <= 5) rational functions are
-// BOTH evaluated and selected, because at 15 % tail probability per draw a warp
-// would execute both sides of a branch anyway.  Only the far tail (p < 1.4e-11)
-// is a real branch.  q is formed from the high word of the draw (a perturbation
-// of < 2^-32, far below single precision), the tail argument min(p, 1-p) from all
-// 64 bits.
+// A branch per draw would make nearly every warp execute both sides (15 % tail
+// probability per draw), so a generator round (16 draws per thread) is transformed
+// in two phases: the central formula (|q| <= 0.425) for all 16 draws, then each
+// lane loops over its OWN tail draws (2.4 on average, so the warp runs the tail
+// code ~6 times per round instead of 16).
 //
-// F64 mode: AS241 in double precision; central region for all draws first, then
-// each lane loops over its own tail draws.
+// F32 mode (the reference AS BUILT, as241.f90:20-25): the central phase handles two
+// draws per packed single-precision instruction (fma.rn.f32x2 -> FFMA2, Blackwell's
+// two-wide FP32 FMA) with the AS241 coefficients as immediates.  q is formed from
+// the high word of the draw (a perturbation of < 2^-32, far below single
+// precision), the tail argument min(p, 1-p) from all 64 bits.
+//
+// F64 mode: AS241 in double precision, same two phases.
 #pragma once
 #include <stdint.h>
 
@@ -94,59 +95,55 @@ __device__ __noinline__ float ppnd_far_tail_f32(float q, float t) {
   return q < 0.0f ? -z : z;
 }
 
-// Two draws -> two normals, single precision (as-built AS241)
-__device__ __forceinline__ void normal2_f32(uint64_t w0, uint64_t w1, float& z0, float& z1) {
+// Phase 1 (F32 mode): the central formula for two draws at once (as241.f90:88-92).
+// tail0/tail1 are set when |q| > 0.425; such draws get their value from
+// normal_tail_f32 afterwards (z0/z1 then hold a finite placeholder).
+__device__ __forceinline__ void normal2_central_f32(uint64_t w0, uint64_t w1, float& z0, float& z1,
+                                                    bool& tail0, bool& tail1) {
   using P = Ppnd;
-  const uint32_t hi0 = (uint32_t)(w0 >> 32), lo0 = (uint32_t)w0;
-  const uint32_t hi1 = (uint32_t)(w1 >> 32), lo1 = (uint32_t)w1;
-  // q = p - 1/2 from the high word
+  const uint32_t hi0 = (uint32_t)(w0 >> 32), hi1 = (uint32_t)(w1 >> 32);
+  // q = p - 1/2 from the high word of the draw
   const uint64_t q2 = fmul2(pack2((float)(int32_t)(hi0 ^ 0x80000000u),
                                   (float)(int32_t)(hi1 ^ 0x80000000u)),
                             HEXO_BC(2.3283064365386963e-10f));  // 2^-32
   float q0, q1;
   unpack2(q2, q0, q1);
-  // v = p (q < 0) or ~p ~ 1 - p (q >= 0) as a 64-bit fraction; vf = v 2^-32
-  const uint32_t f0 = (uint32_t)((int32_t)hi0 >> 31), f1 = (uint32_t)((int32_t)hi1 >> 31);
-  const uint64_t vf2 = ffma2(pack2((float)(lo0 ^ f0), (float)(lo1 ^ f1)),
-                             HEXO_BC(2.3283064365386963e-10f),
-                             pack2((float)(hi0 ^ f0), (float)(hi1 ^ f1)));
-  float vf0, vf1;
-  unpack2(vf2, vf0, vf1);
-  // t = -ln(v 2^-64) = (32 - lg2(vf)) ln2  >= 0
-  const uint64_t t2 = ffma2(pack2(mufu_lg2(vf0), mufu_lg2(vf1)), HEXO_BC(-0.69314718055994530942f),
-                            HEXO_BC(22.180709777918249f));
-  float t0, t1;
-  unpack2(t2, t0, t1);
-  const float r0 = mufu_sqrt(t0), r1 = mufu_sqrt(t1);
-  // central: q A(rc)/B(rc), rc = 0.180625 - q^2     (as241.f90:88-92)
+  tail0 = fabsf(q0) > (float)P::SPLIT1;
+  tail1 = fabsf(q1) > (float)P::SPLIT1;
   const uint64_t rc = pack2(fmaf(-q0, q0, (float)P::CONST1), fmaf(-q1, q1, (float)P::CONST1));
-  uint64_t numc = horner8x2(rc, (float)P::A7, (float)P::A6, (float)P::A5, (float)P::A4,
-                            (float)P::A3, (float)P::A2, (float)P::A1, (float)P::A0);
-  const uint64_t denc = horner8x2(rc, (float)P::B7, (float)P::B6, (float)P::B5, (float)P::B4,
-                                  (float)P::B3, (float)P::B2, (float)P::B1, 1.0f);
-  numc = fmul2(numc, q2);
-  // intermediate tail: C(r-1.6)/D(r-1.6)             (as241.f90:104-109)
-  const uint64_t rm = fadd2(pack2(r0, r1), HEXO_BC(-(float)P::CONST2));
-  const uint64_t numm = horner8x2(rm, (float)P::C7, (float)P::C6, (float)P::C5, (float)P::C4,
-                                  (float)P::C3, (float)P::C2, (float)P::C1, (float)P::C0);
-  const uint64_t denm = horner8x2(rm, (float)P::D7, (float)P::D6, (float)P::D5, (float)P::D4,
-                                  (float)P::D3, (float)P::D2, (float)P::D1, 1.0f);
-  float nc0, nc1, dc0, dc1, nm0, nm1, dm0, dm1;
-  unpack2(numc, nc0, nc1);
-  unpack2(denc, dc0, dc1);
-  unpack2(numm, nm0, nm1);
-  unpack2(denm, dm0, dm1);
-  // sign of q onto the (positive) tail value           (as241.f90:116)
-  nm0 = __uint_as_float(__float_as_uint(nm0) ^ (__float_as_uint(q0) & 0x80000000u));
-  nm1 = __uint_as_float(__float_as_uint(nm1) ^ (__float_as_uint(q1) & 0x80000000u));
-  const bool c0 = fabsf(q0) <= (float)P::SPLIT1, c1 = fabsf(q1) <= (float)P::SPLIT1;
-  const uint64_t z2 = fmul2(pack2(c0 ? nc0 : nm0, c1 ? nc1 : nm1),
-                            pack2(mufu_rcp(c0 ? dc0 : dm0), mufu_rcp(c1 ? dc1 : dm1)));
-  unpack2(z2, z0, z1);
-  if (fmaxf(t0, t1) > 25.0f) {  // r > 5, i.e. p < 1.4e-11: essentially never
-    if (t0 > 25.0f) z0 = ppnd_far_tail_f32(q0, t0);
-    if (t1 > 25.0f) z1 = ppnd_far_tail_f32(q1, t1);
+  uint64_t num = horner8x2(rc, (float)P::A7, (float)P::A6, (float)P::A5, (float)P::A4,
+                           (float)P::A3, (float)P::A2, (float)P::A1, (float)P::A0);
+  const uint64_t den = horner8x2(rc, (float)P::B7, (float)P::B6, (float)P::B5, (float)P::B4,
+                                 (float)P::B3, (float)P::B2, (float)P::B1, 1.0f);
+  num = fmul2(num, q2);
+  float d0, d1;
+  unpack2(den, d0, d1);
+  unpack2(fmul2(num, pack2(mufu_rcp(d0), mufu_rcp(d1))), z0, z1);
+}
+
+// Phase 2 (F32 mode): a draw outside the central region (as241.f90:94-116).  The tail
+// argument min(p, 1-p) uses all 64 bits of the draw.
+__device__ __forceinline__ float normal_tail_f32(uint64_t w) {
+  using P = Ppnd;
+  const uint32_t hi = (uint32_t)(w >> 32), lo = (uint32_t)w;
+  const uint32_t flip = (uint32_t)((int32_t)hi >> 31);  // all ones when p >= 1/2
+  // v = p (p < 1/2) or ~p ~ 1 - p as a 64-bit fraction; vf = v 2^-32
+  const float vf = fmaf((float)(lo ^ flip), 2.3283064365386963e-10f, (float)(hi ^ flip));
+  // t = -ln(v 2^-64) = (32 - lg2(vf)) ln2 >= 0,  r = sqrt(t)
+  const float t = fmaf(mufu_lg2(vf), -0.69314718055994530942f, 22.180709777918249f);
+  float z;
+  if (t > 25.0f) {  // r > 5, i.e. p < 1.4e-11, or p in {0, 1}: essentially never
+    z = ppnd_far_tail_f32(-1.0f, t);  // magnitude; sign applied below
+    z = -z;
+  } else {
+    const float r = mufu_sqrt(t) - (float)P::CONST2;
+    z = horner8<float>(r, (float)P::C7, (float)P::C6, (float)P::C5, (float)P::C4, (float)P::C3,
+                       (float)P::C2, (float)P::C1, (float)P::C0) *
+        mufu_rcp(horner8<float>(r, (float)P::D7, (float)P::D6, (float)P::D5, (float)P::D4,
+                                (float)P::D3, (float)P::D2, (float)P::D1, 1.0f));
   }
+  // sign of q = p - 1/2: negative when the top bit of the draw is clear (as241.f90:116)
+  return __uint_as_float(__float_as_uint(z) ^ (~hi & 0x80000000u));
 }
 
 // ---- double precision ---------------------------------------------------------

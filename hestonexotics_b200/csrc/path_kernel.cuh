@@ -36,6 +36,7 @@ constexpr int kMaxBlock = 256;
 #endif
 constexpr int kMinBlocksPerSM = HEXO_MIN_BLOCKS;  // register budget: 65536 / (256 * this)
 constexpr int kStepsPerRound = 8;  // one shishua round = 16 words = 8 steps
+constexpr int kInlineSegs = 8;     // maturities whose constants travel as kernel parameters
 
 struct PathArgs {
   double v0, S, lnS;
@@ -45,24 +46,31 @@ struct PathArgs {
   uint64_t base_paths;    // every stream runs base_paths paths ...
   uint64_t rem_streams;   // ... and global streams < rem_streams one more
   uint32_t n_seg, n_opts;
-  const SegConst* segs;
+  const SegConst* segs;                // all n_seg segments (device memory)
+  SegConst seg_inline[kInlineSegs];    // the first min(n_seg, kInlineSegs) again, in the
+                                       // kernel's constant bank: uniform operands, no registers
   const double* strikes;
   double* partials;  // [gridDim.x][2*n_opts]
+  double* gacc;      // nullptr: per-warp accumulators in shared memory; else zero-initialised
+                     // [gridDim.x][warps][2*n_opts] in device memory (large option chains,
+                     // where shared-memory accumulators would cost occupancy)
 };
 
 // Shared memory of the path kernel (per block), T = threads, W = warps:
-//   zring  [8][T] pairs (Z_V, Z_X) of the current generator round, float2 (F32
-//                 mode) or double2 (F64 mode)
-//   uring  [8][T] raw variance words of the round (the uniform of the psi >= 1.5
-//                 branch comes from the same word as the normal it replaces)
+//   wring  [8][T] the 16 raw words of the current generator round, one (variance
+//                 word, spot word) pair per step.  Kept because the tail phase of
+//                 the normal transform re-reads them and because the psi >= 1.5
+//                 branch needs the UNIFORM of the variance draw (HSimulation.tpp:72)
+//   zring  [8][T] pairs (Z_V, Z_X) of the round, float2 (F32 mode) / double2 (F64)
 //   exptab [32]   2^(j/32)
 //   fvbuf  [W][32] final values of a warp at a maturity
 //   acc    [W][2][n_opts] lane-owned payoff sums / sums of squares
-__host__ __device__ inline size_t path_kernel_smem(int block, uint32_t n_opts, int normal_mode) {
+__host__ __device__ inline size_t path_kernel_smem(int block, uint32_t n_opts, int normal_mode,
+                                                   bool acc_in_smem = true) {
   const int warps = block / 32;
   const size_t zbytes = (normal_mode == HEXO_NORMAL_F64 ? 16 : 8) * (size_t)kStepsPerRound * block;
-  return zbytes + (size_t)8 * kStepsPerRound * block + 32 * 8 + (size_t)32 * 8 * warps +
-         (size_t)warps * 2 * n_opts * 8;
+  return zbytes + (size_t)16 * kStepsPerRound * block + 32 * 8 + (size_t)32 * 8 * warps +
+         (acc_in_smem ? (size_t)warps * 2 * n_opts * 8 : 0);
 }
 
 // ---- shared-space accessors (32-bit addresses: no generic-pointer arithmetic
@@ -77,6 +85,12 @@ __device__ __forceinline__ uint64_t lds_b64(uint32_t addr) {
   uint64_t v;
   asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(addr));
   return v;
+}
+__device__ __forceinline__ void sts_b64x2(uint32_t addr, uint64_t a, uint64_t b) {
+  asm volatile("st.shared.v2.b64 [%0], {%1, %2};" ::"r"(addr), "l"(a), "l"(b));
+}
+__device__ __forceinline__ void sts_f32(uint32_t addr, float a) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(a));
 }
 __device__ __forceinline__ void sts_f64x2(uint32_t addr, double a, double b) {
   asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(a), "d"(b));
@@ -93,21 +107,33 @@ __device__ __forceinline__ double lds_f64(uint32_t addr) {
   return a;
 }
 
+// Raw words -> normals for one generator round, in two phases (normals.cuh):
+// central formula for all 16 draws, then a per-lane loop over this lane's tail draws.
+//   wcol / zcol : shared addresses of this thread's step-0 slots, wstride / zstride
+//                 the distance between consecutive steps
 template <int NORMAL_MODE>
 struct ZRing;
 
-// F32 mode: both normals of a step in one 8-byte word
 template <>
 struct ZRing<HEXO_NORMAL_F32> {
-  static constexpr int kBytesPerStep = 8;
-  // zcol = shared address of this thread's slot for step 0, stride = T*8
-  static __device__ __forceinline__ void fill(const uint64_t (&o)[16], uint32_t zcol,
-                                              uint32_t stride) {
+  static constexpr int kBytesPerStep = 8;  // float2 (Z_V, Z_X)
+  static __device__ __forceinline__ void fill(const uint64_t (&o)[16], uint32_t wcol,
+                                              uint32_t wstride, uint32_t zcol, uint32_t zstride) {
+    uint32_t tails = 0;
 #pragma unroll
     for (int s = 0; s < kStepsPerRound; ++s) {
       float zv, zx;
-      normal2_f32(o[2 * s], o[2 * s + 1], zv, zx);
-      sts_b64(zcol + s * stride, pack2(zv, zx));
+      bool t0, t1;
+      normal2_central_f32(o[2 * s], o[2 * s + 1], zv, zx, t0, t1);
+      sts_b64(zcol + s * zstride, pack2(zv, zx));
+      if (t0) tails |= 1u << (2 * s);
+      if (t1) tails |= 2u << (2 * s);
+    }
+    while (tails) {
+      const int j = __ffs(tails) - 1;
+      tails &= tails - 1;
+      const uint64_t w = lds_b64(wcol + (j >> 1) * wstride + (j & 1) * 8);
+      sts_f32(zcol + (j >> 1) * zstride + (j & 1) * 4, normal_tail_f32(w));
     }
   }
   static __device__ __forceinline__ void get(uint32_t addr, double& zv, double& zx) {
@@ -118,28 +144,26 @@ struct ZRing<HEXO_NORMAL_F32> {
   }
 };
 
-// F64 mode: central region for every draw, then a per-lane loop over the tails
 template <>
 struct ZRing<HEXO_NORMAL_F64> {
-  static constexpr int kBytesPerStep = 16;
-  static __device__ __forceinline__ void fill(const uint64_t (&o)[16], uint32_t zcol,
-                                              uint32_t stride) {
+  static constexpr int kBytesPerStep = 16;  // double2 (Z_V, Z_X)
+  static __device__ __forceinline__ void fill(const uint64_t (&o)[16], uint32_t wcol,
+                                              uint32_t wstride, uint32_t zcol, uint32_t zstride) {
     uint32_t tails = 0;
 #pragma unroll
     for (int s = 0; s < kStepsPerRound; ++s) {
       bool t0, t1;
       const double zv = normal_central_f64(o[2 * s], t0);
       const double zx = normal_central_f64(o[2 * s + 1], t1);
-      // a tail draw parks its raw word in the slot until the loop below replaces it
-      sts_f64x2(zcol + s * stride, t0 ? __longlong_as_double((long long)o[2 * s]) : zv,
-                t1 ? __longlong_as_double((long long)o[2 * s + 1]) : zx);
-      tails |= (t0 ? 1u : 0u) << (2 * s) | (t1 ? 1u : 0u) << (2 * s + 1);
+      sts_f64x2(zcol + s * zstride, zv, zx);
+      if (t0) tails |= 1u << (2 * s);
+      if (t1) tails |= 2u << (2 * s);
     }
     while (tails) {
       const int j = __ffs(tails) - 1;
       tails &= tails - 1;
-      const uint32_t slot = zcol + (j >> 1) * stride + (j & 1) * 8;
-      sts_f64(slot, normal_tail_f64((uint64_t)__double_as_longlong(lds_f64(slot))));
+      const uint64_t w = lds_b64(wcol + (j >> 1) * wstride + (j & 1) * 8);
+      sts_f64(zcol + (j >> 1) * zstride + (j & 1) * 8, normal_tail_f64(w));
     }
   }
   static __device__ __forceinline__ void get(uint32_t addr, double& zv, double& zx) {
@@ -147,8 +171,9 @@ struct ZRing<HEXO_NORMAL_F64> {
   }
 };
 
-template <int PAYOFF, int NORMAL_MODE>
-__global__ void __launch_bounds__(kMaxBlock, kMinBlocksPerSM) heston_qe_paths_kernel(const PathArgs a) {
+template <int PAYOFF, int NORMAL_MODE, bool INLINE_SEGS>
+__global__ void __launch_bounds__(kMaxBlock, kMinBlocksPerSM)
+heston_qe_paths_kernel(const __grid_constant__ PathArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int T = blockDim.x, nwarps = T >> 5;
@@ -156,20 +181,22 @@ __global__ void __launch_bounds__(kMaxBlock, kMinBlocksPerSM) heston_qe_paths_ke
   constexpr bool kAsian = PAYOFF == HEXO_PAYOFF_ASIAN;
 
   unsigned char* sp = smem_raw;
-  const uint32_t zstride = Ring::kBytesPerStep * T, ustride = 8 * T;
+  const uint32_t zstride = Ring::kBytesPerStep * T, ustride = 16 * T;
+  const uint32_t ucol = smem_addr(sp) + 16 * tid;  // raw (variance, spot) words of each step
+  sp += (size_t)16 * kStepsPerRound * T;
   const uint32_t zcol = smem_addr(sp) + Ring::kBytesPerStep * tid;
   sp += (size_t)Ring::kBytesPerStep * kStepsPerRound * T;
-  const uint32_t ucol = smem_addr(sp) + 8 * tid;  // raw variance words
-  sp += (size_t)8 * kStepsPerRound * T;
   double* exptab = reinterpret_cast<double*>(sp);
   const uint32_t exptab_s = smem_addr(sp);
   sp += 32 * 8;
   double* fvbuf = reinterpret_cast<double*>(sp) + 32 * warp;
   sp += (size_t)32 * 8 * nwarps;
-  double* acc_all = reinterpret_cast<double*>(sp);
+  double* acc_all = a.gacc ? a.gacc + (size_t)blockIdx.x * nwarps * 2 * a.n_opts
+                           : reinterpret_cast<double*>(sp);
   double* my_sum = acc_all + (size_t)warp * 2 * a.n_opts;  // lane-owned slots
   double* my_sq = my_sum + a.n_opts;
-  for (uint32_t j = lane; j < 2 * a.n_opts; j += 32) my_sum[j] = 0.0;
+  if (!a.gacc)
+    for (uint32_t j = lane; j < 2 * a.n_opts; j += 32) my_sum[j] = 0.0;
   exp_table_init(exptab, tid, T);
 
   const uint64_t slot = (uint64_t)blockIdx.x * T + tid;
@@ -182,8 +209,8 @@ __global__ void __launch_bounds__(kMaxBlock, kMinBlocksPerSM) heston_qe_paths_ke
   Shishua rng;
   auto refill = [&](uint64_t (&o)[16]) {
 #pragma unroll
-    for (int s = 0; s < kStepsPerRound; ++s) sts_b64(ucol + s * ustride, o[2 * s]);
-    Ring::fill(o, zcol, zstride);
+    for (int s = 0; s < kStepsPerRound; ++s) sts_b64x2(ucol + s * ustride, o[2 * s], o[2 * s + 1]);
+    Ring::fill(o, ucol, ustride, zcol, zstride);
   };
   {
     uint64_t o[16];
@@ -199,7 +226,8 @@ __global__ void __launch_bounds__(kMaxBlock, kMinBlocksPerSM) heston_qe_paths_ke
     double V = a.v0, lnX = a.lnS, X = a.S, Xprev = a.S;
     double integral = 0.0;  // AAsianCallNonAdaptive::accumulated_value, reset per path (:34)
     for (uint32_t k = 0; k < a.n_seg; ++k) {
-      const SegConst g = a.segs[k];
+      // INLINE_SEGS: read the constants straight from the parameter bank (k is uniform)
+      const SegConst& g = INLINE_SEGS ? a.seg_inline[k] : a.segs[k];
       if (active) {
         const uint32_t n = g.n_steps;
         if (kAsian && k > 0 && n > 0) {

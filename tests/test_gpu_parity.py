@@ -295,7 +295,15 @@ def test_errors(gpu):
     with pytest.raises(_lib.HexoGpuError) as e:
         hx.price(ASIAN, P0, 100.0, chains_of([1.0, 0.5], [[100.0], [100.0]]), 1000, 2, 252)
     assert e.value.code == -2
-    with pytest.raises(_lib.HexoGpuError) as e:
-        hx.price(ASIAN, P0, 100.0, chains_of([1.0], [list(np.linspace(50, 150, 20000))]), 1000,
-                 20000, 16)
-    assert e.value.code == -5
+
+
+def test_very_wide_chain_uses_device_accumulators(gpu):
+    """20 000 strikes do not fit per-warp shared-memory accumulators; the kernel then accumulates
+    in device memory.  Same sums as the oracle on the same streams."""
+    K = list(np.linspace(50, 150, 20000))
+    c = oa.Contract(oa.ASIAN, [0.5], [K], 16)
+    sm, sq = c.price_stream(3, 700, 64, normal_mode=oa.NORMAL_F64)
+    r = hx.price_full(ASIAN, P0, 100.0, chains_of([0.5], [K]), 700, 20000, 16, seed=3,
+                      normal_mode="f64", n_streams=64)
+    assert np.allclose(r.sums[:20000], sm, rtol=1e-10, atol=1e-9)
+    assert np.allclose(r.sums[20000:], sq, rtol=1e-10, atol=1e-9)
