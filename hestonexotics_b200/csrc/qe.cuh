@@ -9,13 +9,14 @@
 // the FP64 pipe:
 //  * everything that depends only on (HParams, step width) is hoisted into
 //    SegConst on the host; the reference recomputes it every step (:58,:75-79);
-//  * the quadratic branch is rewritten with c = sqrt(1 - psi/2):
+//  * the quadratic branch is rewritten without any division.  With
+//    w = m^2 - s^2/2 (so that sqrt(w) = m sqrt(1 - psi/2)):
 //        b^2 = 2/psi - 1 + sqrt(2/psi (2/psi - 1))   (:64)
 //        a   = m / (1 + b^2)                          (:66)
-//    give  a = m (1 - c),  a b^2 = m c,  a b = m sqrt(c (1 - c)),  hence
-//        V' = a (b + Z)^2 = m (c + Z (2 sqrt(c (1-c)) + (1-c) Z))   (:68)
-//    -- one reciprocal and two square roots instead of three divisions and two
-//    square roots, all on the branch-free fast_rcp / fast_sqrt of fastmath.cuh.
+//    give  a b^2 = sqrt(w),  a = m - sqrt(w),  a b = sqrt(sqrt(w) (m - sqrt(w))),  hence
+//        V' = a (b + Z)^2 = sqrt(w) + Z (2 sqrt(sqrt(w) (m - sqrt(w))) + (m - sqrt(w)) Z)   (:68)
+//    -- two square roots instead of three divisions and two square roots, on the
+//    branch-free fast_sqrt of fastmath.cuh; psi < 1.5 is tested as 3 w > s^2/2.
 // The result agrees with the reference arithmetic to ~1e-15 per step
 // (tests: tape replay <= 1e-12 on final values).
 #pragma once
@@ -50,13 +51,14 @@ __device__ __forceinline__ double qe_variance(const SegConst& g, const double V,
                                               const UniformFn& uv) {
   const double m = fma(V, g.D, g.m0);                       // :59
   const double s2h = fabs(fma(V, g.c1h, g.c2h));            // :60  (s^2/2)
-  const double psih = s2h * fast_rcp(m * m);                // :61  (psi/2)
-  // quadratic branch, evaluated unconditionally (NaN when psi/2 > 1, replaced below)
-  const double c = fast_sqrt(1.0 - psih);
-  const double d = 1.0 - c;
-  const double e = fast_sqrt(fma(c, d, kFm.tiny));          // c d >= 0; never exactly 0 for rsqrt
-  double Vn = m * fma(zv, fma(d, zv, e + e), c);            // :64-68
-  if (!(psih < 0.75)) {                                     // :63  psi >= 1.5 (rare)
+  const double w = fma(m, m, -s2h);                         // m^2 (1 - psi/2)
+  // quadratic branch, evaluated unconditionally (NaN when psi > 2, replaced below)
+  const double sw = fast_sqrt(w);                           // a b^2
+  const double dm = m - sw;                                 // a
+  const double me = fast_sqrt(fma(sw, dm, kFm.tiny));       // a b; sw dm >= 0, kept off exact 0
+  double Vn = fma(zv, fma(dm, zv, me + me), sw);            // :64-68
+  if (!(3.0 * w > s2h)) {                                   // :63  psi >= 1.5 (rare)
+    const double psih = s2h / (m * m);
     const double psi = psih + psih;
     const double p = (psi - 1.0) / (psi + 1.0);             // :70
     const double beta = 2.0 / (m * (psi + 1.0));            // :71
