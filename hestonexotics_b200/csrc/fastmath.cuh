@@ -19,7 +19,8 @@ namespace hexo {
 // moves per use inside the step loop.  Living in the constant bank they become
 // free `c[3][..]` operands of DFMA/DADD.
 struct FmConst {
-  double inv720, inv120, inv24, inv6;  // Taylor coefficients of e^r
+  double inv40320, inv5040;            // Taylor coefficients of e^r ...
+  double inv720, inv120, inv24, inv6;  // ...
   double invL;                         // 32/ln2
   double nLhi, nLlo;                   // -(ln2/32) split in two
   double magic;                        // 1.5 * 2^52
@@ -27,6 +28,7 @@ struct FmConst {
   double u_max;                        // largest double below 1
 };
 __constant__ FmConst kFm = {
+    1.0 / 40320.0, 1.0 / 5040.0,
     1.0 / 720.0, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0,
     46.166241308446828384,
     -2.16608493865351192653e-02, -5.96317165397058656257e-12,

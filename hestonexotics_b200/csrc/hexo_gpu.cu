@@ -154,14 +154,19 @@ __global__ void qe_replay_kernel(double v0, double S, double lnS, uint32_t n_seg
     double sumX = 0.0;
     for (uint32_t i = 0; i < n; ++i, ++step) {
       const double uv = t[3 * step + 1];
-      qe_step(g, V, lnX, t[3 * step], [uv]() { return uv; }, t[3 * step + 2]);
-      if (PAYOFF == HEXO_PAYOFF_ASIAN) {
+      const double Vn = qe_variance(g, V, t[3 * step], [uv]() { return uv; });
+      const double delta = qe_logreturn(g, V, Vn, t[3 * step + 2]);
+      V = Vn;
+      if (PAYOFF == HEXO_PAYOFF_ASIAN) {  // same arithmetic as the path kernel
         Xprev = X;
-        X = fast_exp(lnX, exptab);
+        X = grow_spot(X, delta, exptab);
         if (i + 1 < n) sumX += X;
-      } else if (i + 2 >= n) {
-        Xprev = X;
-        X = fast_exp(lnX, exptab);
+      } else {
+        lnX += delta;
+        if (i + 2 >= n) {
+          Xprev = X;
+          X = fast_exp(lnX, exptab);
+        }
       }
     }
     if (PAYOFF == HEXO_PAYOFF_ASIAN && n > 0) integral += g.h * 0.5 * (Xa - Xprev + 2.0 * sumX);

@@ -122,28 +122,31 @@ __device__ __forceinline__ void normal2_central_f32(uint64_t w0, uint64_t w1, fl
 }
 
 // Phase 2 (F32 mode): a draw outside the central region (as241.f90:94-116).  The tail
-// argument min(p, 1-p) uses all 64 bits of the draw.
-__device__ __forceinline__ float normal_tail_f32(uint64_t w) {
+// argument min(p, 1-p) uses all 64 bits of the draw.  Branch-free intermediate-tail
+// formula (:104-109); *t = -ln(min(p, 1-p)) tells the caller whether the far tail
+// (t > 25, i.e. r > 5, p < 1.4e-11, or p in {0,1}) has to replace the value.
+__device__ __forceinline__ float normal_tail_mid_f32(uint64_t w, float& t) {
   using P = Ppnd;
   const uint32_t hi = (uint32_t)(w >> 32), lo = (uint32_t)w;
   const uint32_t flip = (uint32_t)((int32_t)hi >> 31);  // all ones when p >= 1/2
   // v = p (p < 1/2) or ~p ~ 1 - p as a 64-bit fraction; vf = v 2^-32
   const float vf = fmaf((float)(lo ^ flip), 2.3283064365386963e-10f, (float)(hi ^ flip));
   // t = -ln(v 2^-64) = (32 - lg2(vf)) ln2 >= 0,  r = sqrt(t)
-  const float t = fmaf(mufu_lg2(vf), -0.69314718055994530942f, 22.180709777918249f);
-  float z;
-  if (t > 25.0f) {  // r > 5, i.e. p < 1.4e-11, or p in {0, 1}: essentially never
-    z = ppnd_far_tail_f32(-1.0f, t);  // magnitude; sign applied below
-    z = -z;
-  } else {
-    const float r = mufu_sqrt(t) - (float)P::CONST2;
-    z = horner8<float>(r, (float)P::C7, (float)P::C6, (float)P::C5, (float)P::C4, (float)P::C3,
-                       (float)P::C2, (float)P::C1, (float)P::C0) *
-        mufu_rcp(horner8<float>(r, (float)P::D7, (float)P::D6, (float)P::D5, (float)P::D4,
-                                (float)P::D3, (float)P::D2, (float)P::D1, 1.0f));
-  }
+  t = fmaf(mufu_lg2(vf), -0.69314718055994530942f, 22.180709777918249f);
+  const float r = mufu_sqrt(t) - (float)P::CONST2;
+  const float z =
+      horner8<float>(r, (float)P::C7, (float)P::C6, (float)P::C5, (float)P::C4, (float)P::C3,
+                     (float)P::C2, (float)P::C1, (float)P::C0) *
+      mufu_rcp(horner8<float>(r, (float)P::D7, (float)P::D6, (float)P::D5, (float)P::D4,
+                              (float)P::D3, (float)P::D2, (float)P::D1, 1.0f));
   // sign of q = p - 1/2: negative when the top bit of the draw is clear (as241.f90:116)
   return __uint_as_float(__float_as_uint(z) ^ (~hi & 0x80000000u));
+}
+
+// the far tail for the same draw (rare)
+__device__ __noinline__ float normal_tail_far_f32(uint64_t w, float t) {
+  const uint32_t hi = (uint32_t)(w >> 32);
+  return ppnd_far_tail_f32((hi & 0x80000000u) ? 1.0f : -1.0f, t);
 }
 
 // ---- double precision ---------------------------------------------------------

@@ -129,11 +129,24 @@ struct ZRing<HEXO_NORMAL_F32> {
       if (t0) tails |= 1u << (2 * s);
       if (t1) tails |= 2u << (2 * s);
     }
+    // two tail draws per iteration: the two evaluations are independent, which hides the
+    // MUFU (lg2, sqrt, rcp) latencies of this otherwise serial loop
     while (tails) {
-      const int j = __ffs(tails) - 1;
+      const int j0 = __ffs(tails) - 1;
       tails &= tails - 1;
-      const uint64_t w = lds_b64(wcol + (j >> 1) * wstride + (j & 1) * 8);
-      sts_f32(zcol + (j >> 1) * zstride + (j & 1) * 4, normal_tail_f32(w));
+      const bool two = tails != 0;
+      const int j1 = two ? __ffs(tails) - 1 : j0;
+      tails &= tails - 1;
+      const uint64_t w0 = lds_b64(wcol + (j0 >> 1) * wstride + (j0 & 1) * 8);
+      const uint64_t w1 = lds_b64(wcol + (j1 >> 1) * wstride + (j1 & 1) * 8);
+      float t0, t1;
+      float z0 = normal_tail_mid_f32(w0, t0), z1 = normal_tail_mid_f32(w1, t1);
+      if (fmaxf(t0, t1) > 25.0f) {  // far tail: essentially never
+        if (t0 > 25.0f) z0 = normal_tail_far_f32(w0, t0);
+        if (t1 > 25.0f) z1 = normal_tail_far_f32(w1, t1);
+      }
+      sts_f32(zcol + (j0 >> 1) * zstride + (j0 & 1) * 4, z0);
+      if (two) sts_f32(zcol + (j1 >> 1) * zstride + (j1 & 1) * 4, z1);
     }
   }
   static __device__ __forceinline__ void get(uint32_t addr, double& zv, double& zx) {
@@ -238,6 +251,23 @@ heston_qe_paths_kernel(const __grid_constant__ PathArgs a) {
         }
         const double Xa = X;
         double sumX = 0.0;
+        // log-spot half of a step.  Asian: the spot itself is advanced multiplicatively
+        // (X is needed every step, ln X never); European: ln X is accumulated and X = exp(ln X)
+        // only where with_x says so (HSimulation.tpp:80-82)
+        auto spot_half = [&](double Vfrom, double Vto, double zx, auto with_x) {
+          const double delta = qe_logreturn(g, Vfrom, Vto, zx);
+          if (kAsian) {
+            Xprev = X;
+            X = grow_spot(X, delta, exptab_s);
+            sumX += X;
+          } else {
+            lnX += delta;
+            if (decltype(with_x)::value) {
+              Xprev = X;
+              X = fast_exp(lnX, exptab_s);
+            }
+          }
+        };
         // `count` (> 0) steps of this segment, software-pipelined: iteration j does the
         // log-spot / exp half of step j-1 next to the variance half of step j.
         // with_x: also X = exp(ln X) (HSimulation.tpp:81-82)
@@ -267,12 +297,7 @@ heston_qe_paths_kernel(const __grid_constant__ PathArgs a) {
               double zv, zx;
               Ring::get(za, zv, zx);
               // second half of the previous step
-              lnX = qe_logspot(g, lnX, Vold, V, zx_pend);
-              if (decltype(with_x)::value) {
-                Xprev = X;
-                X = fast_exp(lnX, exptab_s);
-                if (kAsian) sumX += X;
-              }
+              spot_half(Vold, V, zx_pend, with_x);
               // first half of this step
               const double Vn = qe_variance(g, V, zv, [ua]() { return u64_to_unit(lds_b64(ua)); });
               Vold = V;
@@ -281,12 +306,7 @@ heston_qe_paths_kernel(const __grid_constant__ PathArgs a) {
             }
           }
           // epilogue: second half of the last step
-          lnX = qe_logspot(g, lnX, Vold, V, zx_pend);
-          if (decltype(with_x)::value) {
-            Xprev = X;
-            X = fast_exp(lnX, exptab_s);
-            if (kAsian) sumX += X;
-          }
+          spot_half(Vold, V, zx_pend, with_x);
         };
         if (kAsian) {
           if (n > 0) run(n, std::true_type{});
