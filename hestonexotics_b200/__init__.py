@@ -5,7 +5,10 @@ from .types import HParams, Option, OptionsChain, TRADING_DAYS, flatten_chains
 from .pricing import (AAsianCallNonAdaptive, EuropeanCallNonAdaptive, HQEAnderson, PriceResult,
                       price, price_full, price_distributed, schedule, shard_range)
 
+from . import swift  # noqa: E402  (host-side semi-analytic European pricer)
+
 __all__ = [
+    "swift",
     "HParams", "Option", "OptionsChain", "TRADING_DAYS", "flatten_chains",
     "AAsianCallNonAdaptive", "EuropeanCallNonAdaptive", "HQEAnderson", "PriceResult",
     "price", "price_full", "price_distributed", "schedule", "shard_range",

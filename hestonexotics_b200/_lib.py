@@ -20,6 +20,8 @@ ABI_SYMBOLS = (
     "hexo_gpu_measure_fp64_peak", "hexo_gpu_plan_create", "hexo_gpu_plan_launch",
     "hexo_gpu_plan_sums_device", "hexo_gpu_plan_stats", "hexo_gpu_plan_destroy",
 )
+# host-only semi-analytic benchmark functions of the same library (no hexo_gpu_ prefix)
+HOST_SYMBOLS = ("hexo_heston_chf", "hexo_swift_default_params", "hexo_swift_price_chain")
 
 HEXO_OK = 0
 PAYOFF_ASIAN, PAYOFF_EUROPEAN = 0, 1
@@ -56,6 +58,12 @@ class HexoGpuStats(C.Structure):
 class HexoSegment(C.Structure):
     _fields_ = [("n_steps", C.c_uint32), ("h", C.c_double), ("w", C.c_double),
                 ("expiry", C.c_double)]
+
+
+class HexoSwiftParams(C.Structure):
+    _fields_ = [("m", C.c_uint32), ("exp2_m", C.c_uint32), ("sqrt_exp2_m", C.c_double),
+                ("lower", C.c_double), ("upper", C.c_double), ("k_1", C.c_int32),
+                ("k_2", C.c_int32), ("J", C.c_uint32)]
 
 
 class HexoGpuError(RuntimeError):
@@ -104,6 +112,14 @@ def load() -> C.CDLL:
     lib.hexo_gpu_replay.argtypes = [C.POINTER(HexoPriceRequest), c_double_p, C.c_uint64,
                                     C.c_uint32, c_double_p]
     lib.hexo_gpu_measure_fp64_peak.argtypes = [c_double_p, C.POINTER(C.c_float)]
+    lib.hexo_heston_chf.argtypes = [C.POINTER(HexoHParams), C.c_double, C.c_double, C.c_double,
+                                    c_double_p]
+    lib.hexo_swift_default_params.argtypes = [C.POINTER(HexoHParams), C.c_double, C.c_double,
+                                              C.c_double, C.c_double, C.c_double, C.c_double,
+                                              C.POINTER(HexoSwiftParams)]
+    lib.hexo_swift_price_chain.argtypes = [C.POINTER(HexoSwiftParams), C.POINTER(HexoHParams),
+                                           C.c_double, C.c_double, C.c_double, c_double_p,
+                                           C.c_uint32, c_double_p, c_double_p]
     if lib.hexo_gpu_abi_version() != 1:
         raise ImportError("libhexo_gpu.so has an unexpected ABI version; rebuild it")
     _lib = lib

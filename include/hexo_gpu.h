@@ -175,6 +175,39 @@ int hexo_gpu_ppnd16(const double *u_in, double *z_out, size_t n, int normal_mode
 int hexo_gpu_replay(const hexo_price_request *req, const double *tape, uint64_t n_paths,
                     uint32_t tape_steps, double *finals_out);
 
+/* ---- semi-analytic European benchmark (host only) ---------
+ * The Heston characteristic function with its analytic gradient and the SWIFT
+ * pricer of the reference, used to benchmark the Monte-Carlo European price and
+ * (in the reference) to calibrate the HParams the path consumes.  No GPU needed. */
+
+/* swift_parameters, src/inc/SWIFT.h:24-48 */
+typedef struct {
+  uint32_t m;         /* wavelet scale                      */
+  uint32_t exp2_m;    /* 2^m                                */
+  double sqrt_exp2_m; /* sqrt(2^m)                          */
+  double lower;       /* lower integration bound            */
+  double upper;       /* upper integration bound            */
+  int32_t k_1, k_2;   /* wavelet translation range          */
+  uint32_t J;         /* Fourier size (power of two)        */
+} hexo_swift_params;
+
+/* HDistribution::chf_chf_grad(u) (src/HDistribution.cpp:52-88): out = (re,im) pairs of
+ * chf and its partials in HParams order v_0, v_m, rho, kappa, sigma; risk-free rate is not
+ * part of the reference's chf. */
+int hexo_heston_chf(const hexo_hparams *p, double tau, double u_re, double u_im, double out[12]);
+
+/* SwiftParameters(distr, S, chain) (src/SWIFT.cpp:21-35); truncation_precision <= 0
+ * selects the reference's release value 1e-7 (SWIFT.cpp:12-16). */
+int hexo_swift_default_params(const hexo_hparams *p, double tau, double risk_free, double S,
+                              double min_strike, double max_strike, double truncation_precision,
+                              hexo_swift_params *params_out);
+
+/* SWIFT::price_opts / price_opts_grad for one chain (src/SWIFT.cpp:87-118).
+ * grad_out (or NULL): [n_strikes][5], partials in HParams order. */
+int hexo_swift_price_chain(const hexo_swift_params *params, const hexo_hparams *p, double tau,
+                           double risk_free, double S, const double *strikes, uint32_t n_strikes,
+                           double *prices_out, double *grad_out);
+
 /* ---- FP64 pipe peak (roofline denominator; not in MEASURED_PEAKS.json) ------
  * Runs a register-resident DFMA chain kernel; returns FP64 flop/s (FMA = 2). */
 int hexo_gpu_measure_fp64_peak(double *flops_out, float *ms_out);

@@ -27,6 +27,11 @@ def test_library_exports_every_declared_symbol(hexo_lib):
     for n in names:
         assert hasattr(hexo_lib, n), f"{n} declared in include/hexo_gpu.h but not exported"
     assert sorted(_lib.ABI_SYMBOLS) == names
+    text = open(os.path.join(ROOT, "include", "hexo_gpu.h")).read()
+    host = sorted(set(re.findall(r"\b(hexo_(?:swift|heston)_\w+)\s*\(", text)))
+    assert host == sorted(_lib.HOST_SYMBOLS)
+    for n in host:
+        assert hasattr(hexo_lib, n), f"{n} declared in include/hexo_gpu.h but not exported"
     assert hexo_lib.hexo_gpu_abi_version() == 1
 
 
