@@ -32,3 +32,29 @@ def test_cpp_dropin_matches_reference_cpu(gpu, kind):
     # chain-major order: within each maturity prices fall with the strike (90, 100, 110)
     g = got.reshape(3, 3)
     assert (np.diff(g, axis=1) < 0).all() and (np.diff(g[:, 1]) > 0).all()
+
+
+def test_cli_demo_prints_reference_format(gpu):
+    """Row f2: `hexo -p asian all <SYM>` (src/Main.cpp:75-96) with a synthetic chain file instead
+    of the Tradier download and fixed HParams instead of the SQLite DB; pricing through
+    price_gpu<>, output loop in the reference's own format."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "hexo_cli_demo")
+    chain = os.path.join(ROOT, "tests", "golden", "synthetic_chain.csv")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/hexo_cli_demo not built (needs the reference tree at build time)")
+    out = subprocess.run([exe, chain], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    lines = out.stdout.strip().splitlines()
+    assert lines[0].startswith("params, v0: 0.04\tv_m: 0.04\trho: -0.7\tkappa: 2\tsigma: 0.5")
+    body = lines[1:]
+    assert len(body) == 9
+    prices = []
+    for ln in body:
+        fields = dict(f.split(": ") for f in ln.split("\t"))
+        assert list(fields) == ["S", "strike", "bid", "ask", "asian-option-price", "volume",
+                                "imp vol", "lb", "expiry time"]
+        prices.append(float(fields["asian-option-price"]))
+        assert float(fields["imp vol"]) > 0.05
+    pr = np.array(prices).reshape(3, 3)
+    assert (np.diff(pr, axis=1) < 0).all()          # falls with the strike within each expiry
+    assert 1.0 < pr[0, 1] < 2.0 and pr[2, 1] > pr[1, 1] > pr[0, 1]   # ATM Asian grows with expiry
