@@ -107,6 +107,12 @@ __device__ __forceinline__ double lds_f64(uint32_t addr) {
   return a;
 }
 
+// makes a value opaque to the compiler and pins it in a register
+__device__ __forceinline__ double pin(double x) {
+  asm volatile("" : "+d"(x));
+  return x;
+}
+
 // Raw words -> normals for one generator round, in two phases (normals.cuh):
 // central formula for all 16 draws, then a per-lane loop over this lane's tail draws.
 //   wcol / zcol : shared addresses of this thread's step-0 slots, wstride / zstride
@@ -240,7 +246,11 @@ heston_qe_paths_kernel(const __grid_constant__ PathArgs a) {
     double integral = 0.0;  // AAsianCallNonAdaptive::accumulated_value, reset per path (:34)
     for (uint32_t k = 0; k < a.n_seg; ++k) {
       // INLINE_SEGS: read the constants straight from the parameter bank (k is uniform)
-      const SegConst& g = INLINE_SEGS ? a.seg_inline[k] : a.segs[k];
+      SegConst g = INLINE_SEGS ? a.seg_inline[k] : a.segs[k];
+      // keep the per-step constants in registers: otherwise ptxas re-loads each of them from
+      // the constant bank (LDC) at every use inside the step loop
+      g.D = pin(g.D); g.m0 = pin(g.m0); g.c1h = pin(g.c1h); g.c2h = pin(g.c2h);
+      g.K0 = pin(g.K0); g.K1 = pin(g.K1); g.K2 = pin(g.K2); g.K3 = pin(g.K3);
       if (active) {
         const uint32_t n = g.n_steps;
         if (kAsian && k > 0 && n > 0) {
