@@ -33,6 +33,7 @@
 
 #include "../../include/hexo_gpu.h"
 #include "path_kernel.cuh"
+#include "path_kernel_ws.cuh"
 
 namespace hexo {
 
@@ -299,6 +300,7 @@ struct Plan {
   void* blob = nullptr;       // [segs | strikes | partials | sums]
   double* sums_dev = nullptr; // inside blob unless caller-supplied
   size_t gacc_bytes = 0;
+  bool ws = false;  // warp-specialised kernel (path_kernel_ws.cuh)
 };
 
 typedef void (*PathKernel)(const PathArgs);
@@ -315,10 +317,28 @@ static PathKernel pick_kernel(int payoff, int normal_mode, uint32_t n_seg) {
                                         : pick_kernel_t<false>(payoff, normal_mode);
 }
 
+typedef void (*PathKernelWs)(const PathArgs, const uint32_t);
+template <bool INL>
+static PathKernelWs pick_ws_kernel_t(int payoff, int normal_mode) {
+  if (payoff == HEXO_PAYOFF_ASIAN)
+    return normal_mode == HEXO_NORMAL_F64 ? heston_qe_paths_ws_kernel<HEXO_PAYOFF_ASIAN, 1, INL>
+                                          : heston_qe_paths_ws_kernel<HEXO_PAYOFF_ASIAN, 0, INL>;
+  return normal_mode == HEXO_NORMAL_F64 ? heston_qe_paths_ws_kernel<HEXO_PAYOFF_EUROPEAN, 1, INL>
+                                        : heston_qe_paths_ws_kernel<HEXO_PAYOFF_EUROPEAN, 0, INL>;
+}
+static PathKernelWs pick_ws_kernel(int payoff, int normal_mode, uint32_t n_seg) {
+  return n_seg <= (uint32_t)kInlineSegs ? pick_ws_kernel_t<true>(payoff, normal_mode)
+                                        : pick_ws_kernel_t<false>(payoff, normal_mode);
+}
+static bool use_ws() {
+  const char* e = getenv("HEXO_WS");
+  return e && atoi(e) != 0;
+}
+
 static uint64_t default_streams(uint64_t n_paths, int n_gpus) {
   // one wave of resident threads per GPU
-  const uint64_t per_gpu =
-      (uint64_t)(g_ctx.ready ? g_ctx.sm_count : 148) * kMinBlocksPerSM * kMaxBlock;
+  const uint64_t per_gpu = (uint64_t)(g_ctx.ready ? g_ctx.sm_count : 148) *
+                           (use_ws() ? kWsMinBlocks * kWsConsumers : kMinBlocksPerSM * kMaxBlock);
   uint64_t s = per_gpu * (uint64_t)std::max(n_gpus, 1);
   if (s > n_paths) s = n_paths;
   return std::max<uint64_t>(s, 1);
@@ -352,14 +372,21 @@ static int plan_create(const hexo_price_request* r, uint64_t stream_begin, uint6
     const int b = atoi(e);
     if (b >= 32 && b <= kMaxBlock && b % 32 == 0) block = b;
   }
-  const size_t smem_budget = std::min(g_ctx.smem_optin, (size_t)(227 * 1024) / kMinBlocksPerSM);
-  const bool acc_in_smem = path_kernel_smem(block, n_opts, r->normal_mode, true) <= smem_budget;
+  p->ws = use_ws();
+  const size_t smem_budget = std::min(
+      g_ctx.smem_optin, (size_t)(227 * 1024) / (p->ws ? kWsMinBlocks : kMinBlocksPerSM));
+  if (p->ws) block = kWsBlock;
+  const int streams_per_block = p->ws ? kWsConsumers : block;  // path-owning threads per block
+  const bool acc_in_smem =
+      (p->ws ? path_kernel_ws_smem(n_opts, r->normal_mode, true)
+             : path_kernel_smem(block, n_opts, r->normal_mode, true)) <= smem_budget;
   p->payoff = r->payoff;
   p->normal_mode = r->normal_mode;
   p->n_opts = n_opts;
   p->block = (uint32_t)block;
-  p->smem = (uint32_t)path_kernel_smem(block, n_opts, r->normal_mode, acc_in_smem);
-  const uint64_t grid64 = (stream_count + block - 1) / block;
+  p->smem = (uint32_t)(p->ws ? path_kernel_ws_smem(n_opts, r->normal_mode, acc_in_smem)
+                             : path_kernel_smem(block, n_opts, r->normal_mode, acc_in_smem));
+  const uint64_t grid64 = (stream_count + streams_per_block - 1) / streams_per_block;
   if (grid64 > 0x7fffffffull) return fail(HEXO_ERR_TOO_LARGE, "too many streams for one launch");
   p->grid = (uint32_t)grid64;
   p->n_streams = r->n_streams;
@@ -370,7 +397,7 @@ static int plan_create(const hexo_price_request* r, uint64_t stream_begin, uint6
   const size_t part_bytes = (size_t)p->grid * 2 * n_opts * sizeof(double);
   const size_t sums_bytes = (size_t)2 * n_opts * sizeof(double);
   const size_t gacc_bytes =
-      acc_in_smem ? 0 : (size_t)p->grid * (block / 32) * 2 * n_opts * sizeof(double);
+      acc_in_smem ? 0 : (size_t)p->grid * (streams_per_block / 32) * 2 * n_opts * sizeof(double);
   if (gacc_bytes > ((size_t)8 << 30))
     return fail(HEXO_ERR_TOO_LARGE, "%u options x %u blocks need %zu bytes of accumulators", n_opts,
                 p->grid, gacc_bytes);
@@ -402,16 +429,26 @@ static int plan_create(const hexo_price_request* r, uint64_t stream_begin, uint6
   a.gacc = acc_in_smem ? nullptr : reinterpret_cast<double*>(base + off_gacc);
   p->gacc_bytes = gacc_bytes;
 
-  PathKernel kern = pick_kernel(p->payoff, p->normal_mode, p->args.n_seg);
-  HEXO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem));
+  if (p->ws) {
+    PathKernelWs kern = pick_ws_kernel(p->payoff, p->normal_mode, p->args.n_seg);
+    HEXO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem));
+  } else {
+    PathKernel kern = pick_kernel(p->payoff, p->normal_mode, p->args.n_seg);
+    HEXO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem));
+  }
   return HEXO_OK;
 }
 
 // enqueue path kernel + reduction; sums land in `sums_out_dev` (or the plan's own buffer)
 static int plan_launch(const Plan* p, cudaStream_t st, double* sums_out_dev) {
-  PathKernel kern = pick_kernel(p->payoff, p->normal_mode, p->args.n_seg);
   if (p->args.gacc) HEXO_CUDA(cudaMemsetAsync(p->args.gacc, 0, p->gacc_bytes, st));
-  kern<<<p->grid, p->block, p->smem, st>>>(p->args);
+  if (p->ws) {
+    PathKernelWs kern = pick_ws_kernel(p->payoff, p->normal_mode, p->args.n_seg);
+    kern<<<p->grid, p->block, p->smem, st>>>(p->args, (uint32_t)p->steps_per_path);
+  } else {
+    PathKernel kern = pick_kernel(p->payoff, p->normal_mode, p->args.n_seg);
+    kern<<<p->grid, p->block, p->smem, st>>>(p->args);
+  }
   HEXO_CUDA(cudaGetLastError());
   const uint32_t n2 = 2 * p->n_opts;
   reduce_partials_kernel<<<(n2 + 127) / 128, 128, 0, st>>>(p->args.partials, p->grid, n2,

@@ -89,6 +89,9 @@ __device__ __forceinline__ uint64_t lds_b64(uint32_t addr) {
 __device__ __forceinline__ void sts_b64x2(uint32_t addr, uint64_t a, uint64_t b) {
   asm volatile("st.shared.v2.b64 [%0], {%1, %2};" ::"r"(addr), "l"(a), "l"(b));
 }
+__device__ __forceinline__ void lds_b64x2(uint32_t addr, uint64_t& a, uint64_t& b) {
+  asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "r"(addr));
+}
 __device__ __forceinline__ void sts_f32(uint32_t addr, float a) {
   asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(a));
 }

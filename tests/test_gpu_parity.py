@@ -179,6 +179,12 @@ FUSED_CASES = [
      60, oa.DEFAULT_PARAMS, 1500, 500),
     ("stiff", ASIAN, oa.ASIAN, [10.0], [[70.0, 100.0, 130.0]], 2520, oa.STIFF_PARAMS, 200, 64),
     ("exp_branch", ASIAN, oa.ASIAN, [1.0], [[100.0]], 64, (0.01, 0.02, -0.3, 0.5, 1.5), 3000, 128),
+    ("twelve_chains", ASIAN, oa.ASIAN, [0.1 * k for k in range(1, 13)], [[95.0, 105.0]] * 12, 40,
+     oa.DEFAULT_PARAMS, 1200, 150),
+    ("euro_twelve_chains", EURO, oa.EUROPEAN, [0.1 * k for k in range(1, 13)], [[100.0]] * 12, 25,
+     oa.DEFAULT_PARAMS, 1200, 97),
+    ("one_step", EURO, oa.EUROPEAN, [1.0], [[100.0]], 1, oa.DEFAULT_PARAMS, 4000, 64),
+    ("one_path", ASIAN, oa.ASIAN, [1.0], [[100.0]], 16, oa.DEFAULT_PARAMS, 1, 1),
     ("one_stream", ASIAN, oa.ASIAN, [1.0], [[100.0]], 32, oa.DEFAULT_PARAMS, 50, 1),
     ("more_streams_than_a_block", EURO, oa.EUROPEAN, [0.5], [[100.0]], 16, oa.DEFAULT_PARAMS,
      5000, 1000),
@@ -201,6 +207,24 @@ def test_fused_kernel_sums_vs_oracle_streams(gpu, case, mode, tol):
     assert np.allclose(res.prices, sm / n_paths, rtol=tol)
     assert res.steps_per_path == c.steps_to_last_expiry()
     assert res.path_steps == n_paths * steps
+
+
+@pytest.mark.parametrize("case", [c for c in FUSED_CASES if c[0] in
+                                  ("asian_1", "euro_same_step", "asian_chain_70_strikes", "exp_branch",
+                                   "twelve_chains", "more_streams_than_a_block")],
+                         ids=lambda c: c[0])
+def test_warp_specialised_variant_same_sums(gpu, case, monkeypatch):
+    """HEXO_WS=1 selects the producer/consumer kernel (path_kernel_ws.cuh): same streams, same
+    arithmetic, so the same sums as the oracle."""
+    monkeypatch.setenv("HEXO_WS", "1")
+    _, scheme, payoff, T, K, steps, params, n_paths, n_streams = case
+    c = oa.Contract(payoff, T, K, steps, params)
+    sm, sq = c.price_stream(seed=7, n_paths=n_paths, n_streams=n_streams, normal_mode=oa.NORMAL_F64)
+    res = hx.price_full(scheme, hx.HParams(*params), 100.0, chains_of(T, K), n_paths, c.n_opts,
+                        steps, seed=7, normal_mode="f64", n_streams=n_streams)
+    n = c.n_opts
+    assert (np.abs(res.sums[:n] - sm) / np.maximum(np.abs(sm), 1e-300)).max() <= 1e-10
+    assert (np.abs(res.sums[n:] - sq) / np.maximum(np.abs(sq), 1e-300)).max() <= 2e-10
 
 
 def test_sharded_streams_add_up(gpu):
