@@ -426,6 +426,10 @@ static int plan_create(const hexo_price_request* r, uint64_t stream_begin, uint6
   for (size_t k = 0; k < segs.size() && k < (size_t)kInlineSegs; ++k) a.seg_inline[k] = segs[k];
   a.strikes = reinterpret_cast<const double*>(base + off_strikes);
   a.partials = reinterpret_cast<double*>(base + off_part);
+  {
+    const char* e = getenv("HEXO_NO_REFILL");
+    a.dev_no_refill = (e && atoi(e) != 0) ? 1u : 0u;
+  }
   a.gacc = acc_in_smem ? nullptr : reinterpret_cast<double*>(base + off_gacc);
   p->gacc_bytes = gacc_bytes;
 

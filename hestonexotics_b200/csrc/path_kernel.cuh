@@ -51,6 +51,8 @@ struct PathArgs {
                                        // kernel's constant bank: uniform operands, no registers
   const double* strikes;
   double* partials;  // [gridDim.x][2*n_opts]
+  uint32_t dev_no_refill;  // development probe (HEXO_NO_REFILL=1): reuse the first generator
+                           // round forever, i.e. time the FP64 step loop alone
   double* gacc;      // nullptr: per-warp accumulators in shared memory; else zero-initialised
                      // [gridDim.x][warps][2*n_opts] in device memory (large option chains,
                      // where shared-memory accumulators would cost occupancy)
@@ -289,9 +291,11 @@ heston_qe_paths_kernel(const __grid_constant__ PathArgs a) {
           bool first = true;
           while (count) {
             if (pos == kStepsPerRound) {
-              uint64_t o[16];
-              rng.round(o);
-              refill(o);
+              if (!a.dev_no_refill) {
+                uint64_t o[16];
+                rng.round(o);
+                refill(o);
+              }
               pos = 0;
             }
             uint32_t m = min(kStepsPerRound - pos, count);

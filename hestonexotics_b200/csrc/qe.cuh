@@ -57,15 +57,20 @@ __device__ __forceinline__ double qe_variance(const SegConst& g, const double V,
   const double dm = m - sw;                                 // a
   const double me = fast_sqrt(fma(sw, dm, kFm.tiny));       // a b; sw dm >= 0, kept off exact 0
   double Vn = fma(zv, fma(dm, zv, me + me), sw);            // :64-68
-  if (!(3.0 * w > s2h)) {                                   // :63  psi >= 1.5 (rare)
-    const double psih = s2h / (m * m);
-    const double psi = psih + psih;
-    const double p = (psi - 1.0) / (psi + 1.0);             // :70
-    const double beta = 2.0 / (m * (psi + 1.0));            // :71
+  if (!(3.0 * w > s2h)) {                                   // :63  psi >= 1.5
+    // Exponential / zero-mass branch (:70-73), a few per cent of the warp-steps, so it is
+    // straight-line code as well.  With q = m^2 (psi + 1) = m^2 + s^2:
+    //   p = (psi-1)/(psi+1),  p < U  <=>  s^2 - m^2 < U q
+    //   beta = 2/(m (psi+1)) = 2 m / q,  1 - p = 2 m^2 / q
+    //   V' = ln((1-p)/(1-U)) / beta = q/(2m) ln(2 m^2 / (q (1-U)))
+    const double m2 = m * m, s2 = s2h + s2h;
+    const double q = m2 + s2;
     // U = 1.0 (probability 2^-54) would make the reference take log(x/0) = inf;
     // clamp to the largest double below 1 instead.
     const double u = fmin(uv(), kFm.u_max);                 // :72
-    Vn = p < u ? log((1.0 - p) / (1.0 - u)) / beta : 0.0;   // :73
+    const double y = (m2 + m2) * fast_rcp(q * (1.0 - u));
+    const double v = 0.5 * q * fast_rcp(m) * fast_log(y);
+    Vn = (s2 - m2 < u * q) ? v : 0.0;                       // :73
   }
   return Vn;
 }
