@@ -161,25 +161,40 @@ __device__ __forceinline__ double normal_central_f64(uint64_t w, bool& tail) {
          fast_rcp(horner8<double>(r, P::B7, P::B6, P::B5, P::B4, P::B3, P::B2, P::B1, 1.0));
 }
 
-// as241.f90:94-116 for a draw already known to be outside the central region
-__device__ __forceinline__ double normal_tail_f64(uint64_t w) {
+// as241.f90:94-116 for a draw already known to be outside the central region: branch-free
+// intermediate tail (:104-109); *rr = sqrt(-ln(min(p,1-p))) tells the caller whether the far
+// tail (rr > 5) or the p in {0,1} case (rr not finite) has to replace the value.
+__device__ __forceinline__ double normal_tail_mid_f64(uint64_t w, double& rr) {
   using P = Ppnd;
   const double p = u64_to_unit(w);
   const double q = p - 0.5;
-  double r = (q < 0.0) ? p : 1.0 - p;
-  if (r <= 0.0) return 0.0;
-  r = fast_sqrt(-log(r));
-  double z;
-  if (r <= P::SPLIT2) {
-    r -= P::CONST2;
-    z = horner8<double>(r, P::C7, P::C6, P::C5, P::C4, P::C3, P::C2, P::C1, P::C0) *
-        fast_rcp(horner8<double>(r, P::D7, P::D6, P::D5, P::D4, P::D3, P::D2, P::D1, 1.0));
-  } else {
-    r -= P::SPLIT2;
-    z = horner8<double>(r, P::E7, P::E6, P::E5, P::E4, P::E3, P::E2, P::E1, P::E0) /
-        horner8<double>(r, P::F7, P::F6, P::F5, P::F4, P::F3, P::F2, P::F1, 1.0);
-  }
+  const double v = (q < 0.0) ? p : 1.0 - p;
+  rr = fast_sqrt(-fast_log(fmax(v, 1e-300)));   // v == 0 -> rr ~ 26 -> far-tail path returns 0
+  const double r = rr - P::CONST2;
+  const double z = horner8<double>(r, P::C7, P::C6, P::C5, P::C4, P::C3, P::C2, P::C1, P::C0) *
+                   fast_rcp(horner8<double>(r, P::D7, P::D6, P::D5, P::D4, P::D3, P::D2, P::D1, 1.0));
   return (q < 0.0) ? -z : z;
+}
+
+// far tail (:110-114) and p in {0,1} (:99-103) for the same draw (rare)
+__device__ __noinline__ double normal_tail_far_f64(uint64_t w, double rr) {
+  using P = Ppnd;
+  const double p = u64_to_unit(w);
+  const double q = p - 0.5;
+  const double v = (q < 0.0) ? p : 1.0 - p;
+  if (v <= 0.0) return 0.0;
+  const double r = rr - P::SPLIT2;
+  const double z = horner8<double>(r, P::E7, P::E6, P::E5, P::E4, P::E3, P::E2, P::E1, P::E0) /
+                   horner8<double>(r, P::F7, P::F6, P::F5, P::F4, P::F3, P::F2, P::F1, 1.0);
+  return (q < 0.0) ? -z : z;
+}
+
+// one draw, both tails
+__device__ __forceinline__ double normal_tail_f64(uint64_t w) {
+  double rr;
+  double z = normal_tail_mid_f64(w, rr);
+  if (rr > Ppnd::SPLIT2) z = normal_tail_far_f64(w, rr);
+  return z;
 }
 
 }  // namespace hexo

@@ -183,11 +183,22 @@ struct ZRing<HEXO_NORMAL_F64> {
       if (t0) tails |= 1u << (2 * s);
       if (t1) tails |= 2u << (2 * s);
     }
-    while (tails) {
-      const int j = __ffs(tails) - 1;
+    while (tails) {  // two tail draws per iteration, as in F32 mode
+      const int j0 = __ffs(tails) - 1;
       tails &= tails - 1;
-      const uint64_t w = lds_b64(wcol + (j >> 1) * wstride + (j & 1) * 8);
-      sts_f64(zcol + (j >> 1) * zstride + (j & 1) * 8, normal_tail_f64(w));
+      const bool two = tails != 0;
+      const int j1 = two ? __ffs(tails) - 1 : j0;
+      tails &= tails - 1;
+      const uint64_t w0 = lds_b64(wcol + (j0 >> 1) * wstride + (j0 & 1) * 8);
+      const uint64_t w1 = lds_b64(wcol + (j1 >> 1) * wstride + (j1 & 1) * 8);
+      double r0, r1;
+      double z0 = normal_tail_mid_f64(w0, r0), z1 = normal_tail_mid_f64(w1, r1);
+      if (fmax(r0, r1) > Ppnd::SPLIT2) {  // far tail: essentially never
+        if (r0 > Ppnd::SPLIT2) z0 = normal_tail_far_f64(w0, r0);
+        if (r1 > Ppnd::SPLIT2) z1 = normal_tail_far_f64(w1, r1);
+      }
+      sts_f64(zcol + (j0 >> 1) * zstride + (j0 & 1) * 8, z0);
+      if (two) sts_f64(zcol + (j1 >> 1) * zstride + (j1 & 1) * 8, z1);
     }
   }
   static __device__ __forceinline__ void get(uint32_t addr, double& zv, double& zx) {
