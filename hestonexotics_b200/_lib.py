@@ -14,7 +14,8 @@ LIB_PATH = os.path.join(HERE, "lib", "libhexo_gpu.so")
 # names of every function include/hexo_gpu.h declares (checked by tests)
 ABI_SYMBOLS = (
     "hexo_gpu_abi_version", "hexo_gpu_init", "hexo_gpu_shutdown", "hexo_gpu_device_count",
-    "hexo_gpu_last_error", "hexo_gpu_schedule", "hexo_gpu_price", "hexo_gpu_price_shard",
+    "hexo_gpu_last_error", "hexo_gpu_schedule", "hexo_gpu_price", "hexo_gpu_price_multi",
+    "hexo_gpu_price_shard",
     "hexo_gpu_price_shard_device", "hexo_gpu_default_streams", "hexo_gpu_shishua_fill",
     "hexo_gpu_shishua_streams", "hexo_gpu_u64_to_unit", "hexo_gpu_ppnd16", "hexo_gpu_replay",
     "hexo_gpu_measure_fp64_peak", "hexo_gpu_plan_create", "hexo_gpu_plan_launch",
@@ -91,6 +92,8 @@ def load() -> C.CDLL:
     lib.hexo_gpu_schedule.argtypes = [c_double_p, C.c_uint32, C.c_uint32, C.POINTER(HexoSegment)]
     lib.hexo_gpu_price.argtypes = [C.POINTER(HexoPriceRequest), c_double_p, c_double_p,
                                    C.POINTER(HexoGpuStats)]
+    lib.hexo_gpu_price_multi.argtypes = [C.POINTER(HexoPriceRequest), C.c_int, c_double_p,
+                                         c_double_p, C.POINTER(HexoGpuStats)]
     lib.hexo_gpu_price_shard.argtypes = [C.POINTER(HexoPriceRequest), C.c_uint64, C.c_uint64,
                                          c_double_p, C.POINTER(HexoGpuStats)]
     lib.hexo_gpu_price_shard_device.argtypes = [C.POINTER(HexoPriceRequest), C.c_uint64, C.c_uint64,

@@ -44,7 +44,8 @@ struct payoff_of<HQEAnderson<ffloat, EuropeanCallNonAdaptive>> {
 struct GpuPriceOptions {
   uint64_t seed = 1;                      // the reference's thread-0 seed (HSimulation.tpp:28)
   int normal_mode = HEXO_NORMAL_F32;      // the reference as built (as241.f90:20-25)
-  uint64_t n_streams = 0;                 // 0 = sized for the device
+  uint64_t n_streams = 0;                 // 0 = sized for the device(s)
+  int n_gpus = 1;                         // devices of this process to spread over; 0 = all
   std::vector<ffloat>* stderr_out = nullptr;  // optional Monte-Carlo standard errors
 };
 
@@ -82,8 +83,9 @@ std::vector<ffloat> price_gpu(const HParams& p, const ffloat S,
   req.n_streams = opt.n_streams;
   std::vector<ffloat> prices(n_opts);
   if (opt.stderr_out) opt.stderr_out->assign(n_opts, 0.0);
-  const int rc = hexo_gpu_price(&req, prices.data(),
-                                opt.stderr_out ? opt.stderr_out->data() : nullptr, nullptr);
+  double* se = opt.stderr_out ? opt.stderr_out->data() : nullptr;
+  const int rc = opt.n_gpus == 1 ? hexo_gpu_price(&req, prices.data(), se, nullptr)
+                                 : hexo_gpu_price_multi(&req, opt.n_gpus, prices.data(), se, nullptr);
   if (rc != HEXO_OK)
     throw std::runtime_error(std::string("price_gpu: ") + hexo_gpu_last_error());
   return prices;

@@ -631,6 +631,84 @@ int hexo_gpu_price(const hexo_price_request* req, double* prices_out, double* st
   return HEXO_OK;
 }
 
+// One process, several GPUs: the single-process form of the multi-GPU path for callers like the
+// reference's CLI, which is one process.  Streams are split over the first n_gpus devices
+// exactly like hx.price_distributed splits them over ranks; the 2*n_opts sums of each device come
+// back over PCIe and are added on the host (16 bytes per option -- no collective needed).
+int hexo_gpu_price_multi(const hexo_price_request* req, int n_gpus, double* prices_out,
+                         double* stderr_out, hexo_gpu_stats* stats) {
+  int rc = check_request(req, true);
+  if (rc) return rc;
+  if (!prices_out) return fail(HEXO_ERR_INVALID_ARGUMENT, "prices_out is NULL");
+  const int n_dev = hexo_gpu_device_count();
+  if (n_dev == 0) return fail(HEXO_ERR_NO_DEVICE, "no CUDA device visible");
+  if (n_gpus <= 0) n_gpus = n_dev;
+  if (n_gpus > n_dev)
+    return fail(HEXO_ERR_INVALID_ARGUMENT, "%d GPUs requested, %d visible", n_gpus, n_dev);
+  int home = 0;
+  HEXO_CUDA(cudaGetDevice(&home));
+  rc = ensure_context();
+  if (rc) return rc;
+  hexo_price_request r = *req;
+  if (r.n_streams == 0) r.n_streams = default_streams(r.n_paths, n_gpus);
+  const uint32_t n_opts = r.strike_offsets[r.n_chains];
+  std::vector<Plan> plans(n_gpus);
+  std::vector<int> used(n_gpus, 0);
+  std::vector<cudaEvent_t> ev0(n_gpus), ev1(n_gpus);
+  const uint64_t base = r.n_streams / n_gpus, rem = r.n_streams % n_gpus;
+  for (int g = 0; g < n_gpus && rc == HEXO_OK; ++g) {  // enqueue everywhere first
+    const uint64_t begin = g * base + std::min<uint64_t>(g, rem), count = base + (g < (int)rem);
+    if (count == 0) continue;
+    if (cudaSetDevice(g) != cudaSuccess) {
+      rc = fail(HEXO_ERR_CUDA, "cudaSetDevice(%d) failed", g);
+      break;
+    }
+    rc = plan_create(&r, begin, count, 0, &plans[g]);
+    if (rc) break;
+    used[g] = 1;
+    cudaEventCreate(&ev0[g]);
+    cudaEventCreate(&ev1[g]);
+    cudaEventRecord(ev0[g], 0);
+    rc = plan_launch(&plans[g], 0, nullptr);
+    cudaEventRecord(ev1[g], 0);
+  }
+  std::vector<double> sums(2 * (size_t)n_opts, 0.0), part(2 * (size_t)n_opts);
+  float ms_max = 0.f;
+  for (int g = 0; g < n_gpus; ++g) {  // then collect
+    if (!used[g]) continue;
+    cudaSetDevice(g);
+    if (rc == HEXO_OK) {
+      cudaError_t e = cudaMemcpy(part.data(), plans[g].sums_dev, part.size() * sizeof(double),
+                                 cudaMemcpyDeviceToHost);
+      if (e != cudaSuccess)
+        rc = fail(HEXO_ERR_CUDA, "device %d: %s", g, cudaGetErrorString(e));
+      else
+        for (size_t j = 0; j < part.size(); ++j) sums[j] += part[j];
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, ev0[g], ev1[g]) == cudaSuccess) ms_max = std::max(ms_max, ms);
+    } else {
+      cudaDeviceSynchronize();
+    }
+    cudaEventDestroy(ev0[g]);
+    cudaEventDestroy(ev1[g]);
+    plan_destroy(&plans[g], 0);
+  }
+  cudaSetDevice(home);
+  if (rc) return rc;
+  fill_stats(plans[0], ms_max, stats);
+  if (stats) stats->kernel_launches = 2 * (uint32_t)n_gpus;
+  const double n = (double)r.n_paths;
+  for (uint32_t j = 0; j < n_opts; ++j) {
+    const double mean = sums[j] / n;
+    prices_out[j] = mean;
+    if (stderr_out) {
+      const double var = n > 1 ? std::max(0.0, (sums[n_opts + j] - n * mean * mean) / (n - 1)) : 0.0;
+      stderr_out[j] = sqrt(var / n);
+    }
+  }
+  return HEXO_OK;
+}
+
 int hexo_gpu_shishua_streams(uint64_t seed, uint64_t first_stream, uint32_t n_streams,
                              uint8_t* bytes_out, size_t bytes_per_stream) {
   if (!bytes_out || n_streams == 0 || bytes_per_stream == 0 || (bytes_per_stream & 127))

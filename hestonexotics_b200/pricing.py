@@ -109,6 +109,20 @@ def price_full(scheme, p: HParams, S: float, all_chains: Sequence[OptionsChain],
                        int(stats.grid), int(stats.block))
 
 
+def price_multi(scheme, p: HParams, S: float, all_chains: Sequence[OptionsChain],
+                n_simulations: int, n_opts: Optional[int], steps: int, *, n_gpus: int = 0,
+                seed: int = 1, normal_mode="f32", n_streams: int = 0):
+    """price<Scheme>() spread over several GPUs of THIS process (hexo_gpu_price_multi); returns
+    (prices, stderr).  n_gpus = 0 uses every visible device."""
+    lib = _lib.load()
+    rq = _Request(scheme, p, S, all_chains, n_simulations, n_opts, steps, seed, normal_mode, n_streams)
+    prices, se = np.zeros(rq.n_opts), np.zeros(rq.n_opts)
+    _lib.check(lib.hexo_gpu_price_multi(C.byref(rq.req), int(n_gpus),
+                                        prices.ctypes.data_as(_lib.c_double_p),
+                                        se.ctypes.data_as(_lib.c_double_p), None))
+    return prices, se
+
+
 def price(scheme, p: HParams, S: float, all_chains: Sequence[OptionsChain], n_simulations: int,
           n_opts: Optional[int], steps: int, **kw) -> np.ndarray:
     """Drop-in for HSimulation::price<Scheme>: returns the n_opts prices, chain-major."""

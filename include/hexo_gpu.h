@@ -124,6 +124,13 @@ int hexo_gpu_schedule(const double *expiries, uint32_t n_chains, uint32_t steps,
 int hexo_gpu_price(const hexo_price_request *req, double *prices_out, double *stderr_out,
                    hexo_gpu_stats *stats);
 
+/* The same call spread over the first n_gpus devices of this process (n_gpus <= 0: all
+ * visible devices): the single-process counterpart of the one-rank-per-GPU path, for callers
+ * like the reference's CLI.  Streams are split over devices like ranks split them; the sums
+ * are added on the host. */
+int hexo_gpu_price_multi(const hexo_price_request *req, int n_gpus, double *prices_out,
+                         double *stderr_out, hexo_gpu_stats *stats);
+
 /* The same path for one shard of the job: streams [stream_begin,
  * stream_begin+stream_count) of req->n_streams (which must be non-zero here).
  * sums_out[0..n_opts) = sum of payoffs, sums_out[n_opts..2 n_opts) = sum of

@@ -244,6 +244,23 @@ def test_sharded_streams_add_up(gpu):
     assert np.allclose(whole, np.concatenate([sm, sq]), rtol=1e-10)
 
 
+def test_single_process_multi_gpu(gpu):
+    """hexo_gpu_price_multi: streams split over the devices of one process give the same sums as
+    one device (same seed, paths and stream count); with one device visible it runs on that one."""
+    n_dev = gpu.hexo_gpu_device_count()
+    T, K = [0.5, 1.0], [[95.0, 100.0], [105.0]]
+    one = hx.price_full(ASIAN, P0, 100.0, chains_of(T, K), 20011, 3, 48, seed=9, n_streams=1000)
+    pr, se = hx.price_multi(ASIAN, P0, 100.0, chains_of(T, K), 20011, 3, 48, n_gpus=0, seed=9,
+                            n_streams=1000)
+    assert np.allclose(pr, one.prices, rtol=1e-12) and np.allclose(se, one.stderr, rtol=1e-9)
+    if n_dev >= 2:
+        pr2, _ = hx.price_multi(ASIAN, P0, 100.0, chains_of(T, K), 20011, 3, 48, n_gpus=2, seed=9,
+                                n_streams=1000)
+        assert np.allclose(pr2, one.prices, rtol=1e-12)
+    with pytest.raises(_lib.HexoGpuError):
+        hx.price_multi(ASIAN, P0, 100.0, chains_of(T, K), 100, 3, 48, n_gpus=n_dev + 1)
+
+
 def test_run_to_run_reproducible(gpu):
     a = hx.price_full(ASIAN, P0, 100.0, chains_of([1.0], [[100.0]]), 20000, 1, 252, seed=5)
     b = hx.price_full(ASIAN, P0, 100.0, chains_of([1.0], [[100.0]]), 20000, 1, 252, seed=5)
