@@ -118,6 +118,11 @@ __device__ __forceinline__ double pin(double x) {
   return x;
 }
 
+__device__ __forceinline__ uint32_t pin32(uint32_t x) {
+  asm volatile("" : "+r"(x));
+  return x;
+}
+
 // Raw words -> normals for one generator round, in two phases (normals.cuh):
 // central formula for all 16 draws, then a per-lane loop over this lane's tail draws.
 //   wcol / zcol : shared addresses of this thread's step-0 slots, wstride / zstride
@@ -216,13 +221,15 @@ heston_qe_paths_kernel(const __grid_constant__ PathArgs a) {
   constexpr bool kAsian = PAYOFF == HEXO_PAYOFF_ASIAN;
 
   unsigned char* sp = smem_raw;
-  const uint32_t zstride = Ring::kBytesPerStep * T, ustride = 16 * T;
-  const uint32_t ucol = smem_addr(sp) + 16 * tid;  // raw (variance, spot) words of each step
+  // pin32: keep the ring addresses in registers; otherwise ptxas re-derives them from
+  // %tid / %ntid / the shared window base inside the step and tail loops (~20 instructions)
+  const uint32_t zstride = pin32(Ring::kBytesPerStep * T), ustride = pin32(16 * T);
+  const uint32_t ucol = pin32(smem_addr(sp) + 16 * tid);  // raw (variance, spot) words per step
   sp += (size_t)16 * kStepsPerRound * T;
-  const uint32_t zcol = smem_addr(sp) + Ring::kBytesPerStep * tid;
+  const uint32_t zcol = pin32(smem_addr(sp) + Ring::kBytesPerStep * tid);
   sp += (size_t)Ring::kBytesPerStep * kStepsPerRound * T;
   double* exptab = reinterpret_cast<double*>(sp);
-  const uint32_t exptab_s = smem_addr(sp);
+  const uint32_t exptab_s = pin32(smem_addr(sp));
   sp += 32 * 8;
   double* fvbuf = reinterpret_cast<double*>(sp) + 32 * warp;
   sp += (size_t)32 * 8 * nwarps;
