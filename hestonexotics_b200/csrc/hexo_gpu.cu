@@ -33,6 +33,7 @@
 
 #include "../../include/hexo_gpu.h"
 #include "path_kernel.cuh"
+#include "path_kernel_il.cuh"
 #include "path_kernel_ws.cuh"
 
 namespace hexo {
@@ -301,6 +302,7 @@ struct Plan {
   double* sums_dev = nullptr; // inside blob unless caller-supplied
   size_t gacc_bytes = 0;
   bool ws = false;  // warp-specialised kernel (path_kernel_ws.cuh)
+  bool il = false;  // interleaved look-ahead kernel (path_kernel_il.cuh)
 };
 
 typedef void (*PathKernel)(const PathArgs);
@@ -329,6 +331,22 @@ static PathKernelWs pick_ws_kernel_t(int payoff, int normal_mode) {
 static PathKernelWs pick_ws_kernel(int payoff, int normal_mode, uint32_t n_seg) {
   return n_seg <= (uint32_t)kInlineSegs ? pick_ws_kernel_t<true>(payoff, normal_mode)
                                         : pick_ws_kernel_t<false>(payoff, normal_mode);
+}
+template <bool INL>
+static PathKernel pick_il_kernel_t(int payoff, int normal_mode) {
+  if (payoff == HEXO_PAYOFF_ASIAN)
+    return normal_mode == HEXO_NORMAL_F64 ? heston_qe_paths_il_kernel<HEXO_PAYOFF_ASIAN, 1, INL>
+                                          : heston_qe_paths_il_kernel<HEXO_PAYOFF_ASIAN, 0, INL>;
+  return normal_mode == HEXO_NORMAL_F64 ? heston_qe_paths_il_kernel<HEXO_PAYOFF_EUROPEAN, 1, INL>
+                                        : heston_qe_paths_il_kernel<HEXO_PAYOFF_EUROPEAN, 0, INL>;
+}
+static PathKernel pick_il_kernel(int payoff, int normal_mode, uint32_t n_seg) {
+  return n_seg <= (uint32_t)kInlineSegs ? pick_il_kernel_t<true>(payoff, normal_mode)
+                                        : pick_il_kernel_t<false>(payoff, normal_mode);
+}
+static bool use_il() {
+  const char* e = getenv("HEXO_IL");
+  return e && atoi(e) != 0;
 }
 static bool use_ws() {
   const char* e = getenv("HEXO_WS");
@@ -376,16 +394,19 @@ static int plan_create(const hexo_price_request* r, uint64_t stream_begin, uint6
   const size_t smem_budget = std::min(
       g_ctx.smem_optin, (size_t)(227 * 1024) / (p->ws ? kWsMinBlocks : kMinBlocksPerSM));
   if (p->ws) block = kWsBlock;
+  p->il = !p->ws && use_il();
   const int streams_per_block = p->ws ? kWsConsumers : block;  // path-owning threads per block
-  const bool acc_in_smem =
-      (p->ws ? path_kernel_ws_smem(n_opts, r->normal_mode, true)
-             : path_kernel_smem(block, n_opts, r->normal_mode, true)) <= smem_budget;
+  auto smem_of = [&](bool acc) {
+    return p->ws   ? path_kernel_ws_smem(n_opts, r->normal_mode, acc)
+           : p->il ? path_kernel_il_smem(block, n_opts, r->normal_mode, acc)
+                   : path_kernel_smem(block, n_opts, r->normal_mode, acc);
+  };
+  const bool acc_in_smem = smem_of(true) <= smem_budget;
   p->payoff = r->payoff;
   p->normal_mode = r->normal_mode;
   p->n_opts = n_opts;
   p->block = (uint32_t)block;
-  p->smem = (uint32_t)(p->ws ? path_kernel_ws_smem(n_opts, r->normal_mode, acc_in_smem)
-                             : path_kernel_smem(block, n_opts, r->normal_mode, acc_in_smem));
+  p->smem = (uint32_t)smem_of(acc_in_smem);
   const uint64_t grid64 = (stream_count + streams_per_block - 1) / streams_per_block;
   if (grid64 > 0x7fffffffull) return fail(HEXO_ERR_TOO_LARGE, "too many streams for one launch");
   p->grid = (uint32_t)grid64;
@@ -437,7 +458,8 @@ static int plan_create(const hexo_price_request* r, uint64_t stream_begin, uint6
     PathKernelWs kern = pick_ws_kernel(p->payoff, p->normal_mode, p->args.n_seg);
     HEXO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem));
   } else {
-    PathKernel kern = pick_kernel(p->payoff, p->normal_mode, p->args.n_seg);
+    PathKernel kern = p->il ? pick_il_kernel(p->payoff, p->normal_mode, p->args.n_seg)
+                            : pick_kernel(p->payoff, p->normal_mode, p->args.n_seg);
     HEXO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem));
   }
   return HEXO_OK;
@@ -450,7 +472,8 @@ static int plan_launch(const Plan* p, cudaStream_t st, double* sums_out_dev) {
     PathKernelWs kern = pick_ws_kernel(p->payoff, p->normal_mode, p->args.n_seg);
     kern<<<p->grid, p->block, p->smem, st>>>(p->args, (uint32_t)p->steps_per_path);
   } else {
-    PathKernel kern = pick_kernel(p->payoff, p->normal_mode, p->args.n_seg);
+    PathKernel kern = p->il ? pick_il_kernel(p->payoff, p->normal_mode, p->args.n_seg)
+                            : pick_kernel(p->payoff, p->normal_mode, p->args.n_seg);
     kern<<<p->grid, p->block, p->smem, st>>>(p->args);
   }
   HEXO_CUDA(cudaGetLastError());

@@ -145,8 +145,24 @@ struct ZRing<HEXO_NORMAL_F32> {
       if (t0) tails |= 1u << (2 * s);
       if (t1) tails |= 2u << (2 * s);
     }
-    // two tail draws per iteration: the two evaluations are independent, which hides the
-    // MUFU (lg2, sqrt, rcp) latencies of this otherwise serial loop
+    tail_phase(tails, wcol, wstride, zcol, zstride);
+  }
+  // one (central normals, tail flag) pair of a step, for kernels that spread the central phase
+  // over the step loop: returns the two tail bits
+  static __device__ __forceinline__ uint32_t central_step(uint32_t waddr, uint32_t zaddr) {
+    uint64_t w0, w1;
+    lds_b64x2(waddr, w0, w1);
+    float zv, zx;
+    bool t0, t1;
+    normal2_central_f32(w0, w1, zv, zx, t0, t1);
+    sts_b64(zaddr, pack2(zv, zx));
+    return (t0 ? 1u : 0u) | (t1 ? 2u : 0u);
+  }
+  // two tail draws per iteration: the two evaluations are independent, which hides the
+  // MUFU (lg2, sqrt, rcp) latencies of this otherwise serial loop
+  static __device__ __forceinline__ void tail_phase(uint32_t tails, uint32_t wcol,
+                                                    uint32_t wstride, uint32_t zcol,
+                                                    uint32_t zstride) {
     while (tails) {
       const int j0 = __ffs(tails) - 1;
       tails &= tails - 1;
@@ -188,6 +204,20 @@ struct ZRing<HEXO_NORMAL_F64> {
       if (t0) tails |= 1u << (2 * s);
       if (t1) tails |= 2u << (2 * s);
     }
+    tail_phase(tails, wcol, wstride, zcol, zstride);
+  }
+  static __device__ __forceinline__ uint32_t central_step(uint32_t waddr, uint32_t zaddr) {
+    uint64_t w0, w1;
+    lds_b64x2(waddr, w0, w1);
+    bool t0, t1;
+    const double zv = normal_central_f64(w0, t0);
+    const double zx = normal_central_f64(w1, t1);
+    sts_f64x2(zaddr, zv, zx);
+    return (t0 ? 1u : 0u) | (t1 ? 2u : 0u);
+  }
+  static __device__ __forceinline__ void tail_phase(uint32_t tails, uint32_t wcol,
+                                                    uint32_t wstride, uint32_t zcol,
+                                                    uint32_t zstride) {
     while (tails) {  // two tail draws per iteration, as in F32 mode
       const int j0 = __ffs(tails) - 1;
       tails &= tails - 1;

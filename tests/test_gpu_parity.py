@@ -213,10 +213,12 @@ def test_fused_kernel_sums_vs_oracle_streams(gpu, case, mode, tol):
                                   ("asian_1", "euro_same_step", "asian_chain_70_strikes", "exp_branch",
                                    "twelve_chains", "more_streams_than_a_block")],
                          ids=lambda c: c[0])
-def test_warp_specialised_variant_same_sums(gpu, case, monkeypatch):
-    """HEXO_WS=1 selects the producer/consumer kernel (path_kernel_ws.cuh): same streams, same
-    arithmetic, so the same sums as the oracle."""
-    monkeypatch.setenv("HEXO_WS", "1")
+@pytest.mark.parametrize("variant", ["HEXO_WS", "HEXO_IL"])
+def test_experimental_kernel_variants_same_sums(gpu, case, variant, monkeypatch):
+    """HEXO_WS=1 selects the producer/consumer kernel (path_kernel_ws.cuh), HEXO_IL=1 the
+    interleaved look-ahead kernel (path_kernel_il.cuh): same streams, same arithmetic, so the
+    same sums as the oracle."""
+    monkeypatch.setenv(variant, "1")
     _, scheme, payoff, T, K, steps, params, n_paths, n_streams = case
     c = oa.Contract(payoff, T, K, steps, params)
     sm, sq = c.price_stream(seed=7, n_paths=n_paths, n_streams=n_streams, normal_mode=oa.NORMAL_F64)
