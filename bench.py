@@ -290,11 +290,17 @@ def run_ours(args):
             "gpu_launches": 2 * args.steps,
             "roofline": {
                 "bound": "fp64", "achieved": achieved / 1e12, "peak": fl.value / 1e12,
-                "unit": "TFLOP/s", "frac": achieved / fl.value, "traffic": None,
+                "unit": "TFLOP/s", "frac": achieved / fl.value,
+                # dram__bytes_read.sum + dram__bytes_write.sum of the path kernel in the round-1
+                # `ncu --set full` capture (profiles/r01_path_kernel_ncu_raw_final.csv, a
+                # 4.1e9-path-step launch): 60 928 B read, 0 B written -- code and constants only,
+                # it does not grow with the number of paths
+                "traffic": 60928,
                 "note": "achieved = 100 algorithmic FP64 flop per path-step (SURVEY 8d) x path-steps "
                         "of one GPU / mean path-kernel time (CUDA events); peak = DFMA peak measured "
                         "in this run (hexo_gpu_measure_fp64_peak; MEASURED_PEAKS.json has no FP64 "
-                        "entry); HBM traffic is ~0 by design",
+                        "entry); bound is the FP64 ALU pipe (SURVEY 8d), not HBM or tensor: DRAM "
+                        "traffic (bytes per launch, from ncu) is ~0 by design",
                 "kernel": "heston_qe_paths_kernel", "kernel_ms": kernel_ms,
             },
         }
