@@ -281,7 +281,10 @@ heston_qe_paths_kernel(const __grid_constant__ PathArgs a) {
   Shishua rng;
   auto refill = [&](uint64_t (&o)[16]) {
 #pragma unroll
-    for (int s = 0; s < kStepsPerRound; ++s) sts_b64x2(ucol + s * ustride, o[2 * s], o[2 * s + 1]);
+    for (int s = 0; s < kStepsPerRound; ++s) {  // two 64-bit stores: a 128-bit store would need
+      sts_b64(ucol + s * ustride, o[2 * s]);      // the four words moved into an aligned quad
+      sts_b64(ucol + s * ustride + 8, o[2 * s + 1]);
+    }
     Ring::fill(o, ucol, ustride, zcol, zstride);
   };
   {
@@ -317,10 +320,11 @@ heston_qe_paths_kernel(const __grid_constant__ PathArgs a) {
         // log-spot half of a step.  Asian: the spot itself is advanced multiplicatively
         // (X is needed every step, ln X never); European: ln X is accumulated and X = exp(ln X)
         // only where with_x says so (HSimulation.tpp:80-82)
-        auto spot_half = [&](double Vfrom, double Vto, double zx, auto with_x) {
+        // keep_prev: remember X before the step (only the last step of a run needs it)
+        auto spot_half = [&](double Vfrom, double Vto, double zx, auto with_x, bool keep_prev) {
           const double delta = qe_logreturn(g, Vfrom, Vto, zx);
           if (kAsian) {
-            Xprev = X;
+            if (keep_prev) Xprev = X;
             X = grow_spot(X, delta, exptab_s);
             sumX += X;
           } else {
@@ -358,11 +362,14 @@ heston_qe_paths_kernel(const __grid_constant__ PathArgs a) {
               V = qe_variance(g, Vold, zv, [ua]() { return u64_to_unit(lds_b64(ua)); });
               --m, za += zstride, ua += ustride;
             }
+            // unrolled by two so that the loop-carried rotation (Vold <- V <- V', Z_X) becomes
+            // register renaming instead of moves
+#pragma unroll 2
             for (; m; --m, za += zstride, ua += ustride) {
               double zv, zx;
               Ring::get(za, zv, zx);
               // second half of the previous step
-              spot_half(Vold, V, zx_pend, with_x);
+              spot_half(Vold, V, zx_pend, with_x, !kAsian);
               // first half of this step
               const double Vn = qe_variance(g, V, zv, [ua]() { return u64_to_unit(lds_b64(ua)); });
               Vold = V;
@@ -371,7 +378,7 @@ heston_qe_paths_kernel(const __grid_constant__ PathArgs a) {
             }
           }
           // epilogue: second half of the last step
-          spot_half(Vold, V, zx_pend, with_x);
+          spot_half(Vold, V, zx_pend, with_x, true);
         };
         if (kAsian) {
           if (n > 0) run(n, std::true_type{});
