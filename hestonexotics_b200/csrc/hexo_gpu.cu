@@ -244,6 +244,17 @@ static int check_request(const hexo_price_request* r, bool need_strikes) {
     return fail(HEXO_ERR_INVALID_ARGUMENT, "unknown payoff %d", r->payoff);
   if (r->normal_mode != HEXO_NORMAL_F32 && r->normal_mode != HEXO_NORMAL_F64)
     return fail(HEXO_ERR_INVALID_ARGUMENT, "unknown normal_mode %d", r->normal_mode);
+  // The reference divides by kappa and sigma (HSimulation.tpp:60,75-77) and takes log(S) (:90);
+  // it would silently produce NaN prices.  Refuse instead.
+  const hexo_hparams& p = r->p;
+  if (!(std::isfinite(r->S) && r->S > 0.0))
+    return fail(HEXO_ERR_INVALID_ARGUMENT, "spot S must be positive and finite");
+  if (!(std::isfinite(p.v_0) && p.v_0 >= 0.0 && std::isfinite(p.v_m) && p.v_m >= 0.0))
+    return fail(HEXO_ERR_INVALID_ARGUMENT, "v_0 and v_m must be finite and non-negative");
+  if (!(std::isfinite(p.kappa) && p.kappa > 0.0 && std::isfinite(p.sigma) && p.sigma > 0.0))
+    return fail(HEXO_ERR_INVALID_ARGUMENT, "kappa and sigma must be positive and finite");
+  if (!(p.rho >= -1.0 && p.rho <= 1.0))
+    return fail(HEXO_ERR_INVALID_ARGUMENT, "rho must lie in [-1, 1]");
   if (need_strikes) {
     if (!r->strike_offsets || !r->strikes)
       return fail(HEXO_ERR_INVALID_ARGUMENT, "strike_offsets / strikes is NULL");
@@ -253,6 +264,9 @@ static int check_request(const hexo_price_request* r, bool need_strikes) {
         return fail(HEXO_ERR_INVALID_ARGUMENT, "strike_offsets must be non-decreasing");
     if (r->strike_offsets[r->n_chains] == 0) return fail(HEXO_ERR_INVALID_ARGUMENT, "no options");
     if (r->n_paths == 0) return fail(HEXO_ERR_INVALID_ARGUMENT, "n_paths must be > 0");
+    for (uint32_t j = 0; j < r->strike_offsets[r->n_chains]; ++j)
+      if (!std::isfinite(r->strikes[j]))
+        return fail(HEXO_ERR_INVALID_ARGUMENT, "strike %u is not finite", j);
   }
   return HEXO_OK;
 }

@@ -99,6 +99,27 @@ def test_request_validation_without_gpu(hexo_lib):
                  normal_mode="f16")
 
 
+def test_parameter_validation_is_done_before_touching_the_gpu(hexo_lib):
+    """Bad model parameters are refused with HEXO_ERR_INVALID_ARGUMENT (the reference would
+    divide by kappa / sigma or take log(S) and return NaN prices)."""
+    ch = [hx.OptionsChain.from_strikes(1.0, [100.0])]
+    A = hx.HQEAnderson(hx.AAsianCallNonAdaptive)
+    good = dict(v_0=0.04, v_m=0.04, rho=-0.7, kappa=2.0, sigma=0.5)
+    for bad in (dict(kappa=0.0), dict(sigma=0.0), dict(sigma=-1.0), dict(rho=1.5), dict(v_0=-0.1),
+                dict(v_m=float("nan")), dict(kappa=float("inf"))):
+        with pytest.raises(_lib.HexoGpuError) as e:
+            hx.price(A, hx.HParams(**{**good, **bad}), 100.0, ch, 1000, 1, 16)
+        assert e.value.code == -1, bad
+    for S in (0.0, -5.0, float("nan")):
+        with pytest.raises(_lib.HexoGpuError) as e:
+            hx.price(A, hx.HParams(**good), S, ch, 1000, 1, 16)
+        assert e.value.code == -1
+    with pytest.raises(_lib.HexoGpuError) as e:
+        hx.price(A, hx.HParams(**good), 100.0, [hx.OptionsChain.from_strikes(1.0, [float("nan")])],
+                 1000, 1, 16)
+    assert e.value.code == -1
+
+
 def test_no_cpu_fallback(hexo_lib):
     """Without a CUDA device the compute entry points must fail, not compute."""
     if hexo_lib.hexo_gpu_device_count() > 0:

@@ -19,7 +19,7 @@ BIN = os.path.join(ROOT, "oracle", "_ref", "hexo_dropin")
 def test_cpp_dropin_matches_reference_cpu(gpu, kind):
     if not os.path.exists(BIN):
         pytest.skip("oracle/_ref/hexo_dropin not built (needs the reference tree at build time)")
-    n_cpu, n_gpu = 20000, 2_000_000
+    n_cpu, n_gpu = 100000, 4_000_000
     out = subprocess.run([BIN, kind, str(n_cpu), str(n_gpu), "100"], capture_output=True, text=True,
                          timeout=300)
     assert out.returncode == 0, out.stdout + out.stderr

@@ -318,6 +318,41 @@ def test_cfg3_chain_monotone_and_consistent(gpu):
     assert np.abs(z[np.isfinite(z)]).max() < 4.5
 
 
+def test_cfg3_full_size_chain(gpu):
+    """cfg3 at full size: 64 strikes x 8 maturities, 1e7 paths x 252 steps, once as one 8-chain call
+    (the reference's multi-chain semantics: the step width switches at every expiry) and the first
+    maturity again as a single-chain call on other streams."""
+    T = [0.25 * k for k in range(1, 9)]
+    K = [list(np.linspace(70, 130, 64))] * 8
+    r = hx.price_full(ASIAN, P0, 100.0, chains_of(T, K), 10_000_000, 512, 252, seed=2)
+    pr = r.prices.reshape(8, 64)
+    assert (np.diff(pr, axis=1) < 0).all()                 # decreasing in the strike
+    assert (np.diff(pr[:, 32:], axis=0) > 0).all()         # OTM/ATM Asian calls grow with maturity
+    assert r.steps_per_path == 253 + 126 + 84 + 63 + 51 + 42 + 36 + 32   # SURVEY Appendix B-3
+    one = hx.price_full(ASIAN, P0, 100.0, chains_of(T[:1], K[:1]), 10_000_000, 64, 252, seed=3)
+    se = np.hypot(r.stderr[:64], one.stderr)
+    ok = se > 0
+    assert np.abs((pr[0] - one.prices)[ok] / se[ok]).max() < 4.5
+
+
+def test_cfg5_full_size_stiff_asian_chain(gpu):
+    """cfg5 at full size on one GPU: kappa=20, sigma=1, rho=-0.95, T=10, 2520 steps, 64 strikes,
+    1e8 paths (2.5e11 path-steps).  Size-independent properties: prices fall with the strike, the
+    arithmetic Asian call is below the European call of the same strike (r = 0, Jensen), and the
+    European leg of the same model matches the closed form."""
+    p = hx.HParams(*oa.STIFF_PARAMS)
+    K = list(np.linspace(70, 130, 64))
+    a = hx.price_full(ASIAN, p, 100.0, chains_of([10.0], [K]), 100_000_000, 64, 2520, seed=1)
+    assert a.steps_per_path == 2520 and a.path_steps == 100_000_000 * 2520
+    assert (np.diff(a.prices) < 0).all() and (a.stderr > 0).all()
+    e = hx.price_full(EURO, p, 100.0, chains_of([10.0], [K]), 4_000_000, 64, 2520, seed=2)
+    assert (a.prices < e.prices + 4 * np.hypot(a.stderr, e.stderr)).all()
+    cf = heston_call(100, 100, 10.0, *oa.STIFF_PARAMS, r=0.0)
+    j = int(np.argmin(np.abs(np.array(K) - 100.0)))
+    cfj = heston_call(100, K[j], 10.0, *oa.STIFF_PARAMS, r=0.0)
+    assert abs(e.prices[j] - cfj) <= 3.5 * e.stderr[j], (e.prices[j], cfj, e.stderr[j], cf)
+
+
 def test_cfg5_stiff_european_vs_closed_form(gpu):
     """cfg5 parameters (kappa=20, sigma=1, rho=-0.95), T=10, 2520 steps, European leg against the
     closed form 24.50401."""
