@@ -20,6 +20,7 @@ ABI_SYMBOLS = (
     "hexo_gpu_shishua_streams", "hexo_gpu_u64_to_unit", "hexo_gpu_ppnd16", "hexo_gpu_replay",
     "hexo_gpu_measure_fp64_peak", "hexo_gpu_plan_create", "hexo_gpu_plan_launch",
     "hexo_gpu_plan_sums_device", "hexo_gpu_plan_stats", "hexo_gpu_plan_destroy",
+    "hexo_gpu_philox4x32", "hexo_gpu_philox_streams",
 )
 # host-only semi-analytic benchmark functions of the same library (no hexo_gpu_ prefix)
 HOST_SYMBOLS = ("hexo_heston_chf", "hexo_swift_default_params", "hexo_swift_price_chain")
@@ -27,6 +28,7 @@ HOST_SYMBOLS = ("hexo_heston_chf", "hexo_swift_default_params", "hexo_swift_pric
 HEXO_OK = 0
 PAYOFF_ASIAN, PAYOFF_EUROPEAN = 0, 1
 NORMAL_F32, NORMAL_F64 = 0, 1
+RNG_SHISHUA, RNG_PHILOX = 0, 1
 
 c_double_p = C.POINTER(C.c_double)
 c_uint32_p = C.POINTER(C.c_uint32)
@@ -44,7 +46,7 @@ class HexoPriceRequest(C.Structure):
         ("p", HexoHParams), ("S", C.c_double), ("payoff", C.c_int32), ("n_chains", C.c_uint32),
         ("expiries", c_double_p), ("strike_offsets", c_uint32_p), ("strikes", c_double_p),
         ("n_paths", C.c_uint64), ("steps", C.c_uint32), ("seed", C.c_uint64),
-        ("normal_mode", C.c_int32), ("n_streams", C.c_uint64),
+        ("normal_mode", C.c_int32), ("rng_mode", C.c_int32), ("n_streams", C.c_uint64),
     ]
 
 
@@ -110,6 +112,9 @@ def load() -> C.CDLL:
     lib.hexo_gpu_shishua_fill.argtypes = [c_uint64_p, c_uint8_p, C.c_size_t]
     lib.hexo_gpu_shishua_streams.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, c_uint8_p,
                                              C.c_size_t]
+    lib.hexo_gpu_philox4x32.argtypes = [c_uint32_p, c_uint32_p, c_uint32_p, C.c_size_t]
+    lib.hexo_gpu_philox_streams.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, c_uint64_p,
+                                            C.c_size_t]
     lib.hexo_gpu_u64_to_unit.argtypes = [c_uint64_p, c_double_p, C.c_size_t]
     lib.hexo_gpu_ppnd16.argtypes = [c_double_p, c_double_p, C.c_size_t, C.c_int]
     lib.hexo_gpu_replay.argtypes = [C.POINTER(HexoPriceRequest), c_double_p, C.c_uint64,
@@ -123,7 +128,7 @@ def load() -> C.CDLL:
     lib.hexo_swift_price_chain.argtypes = [C.POINTER(HexoSwiftParams), C.POINTER(HexoHParams),
                                            C.c_double, C.c_double, C.c_double, c_double_p,
                                            C.c_uint32, c_double_p, c_double_p]
-    if lib.hexo_gpu_abi_version() != 1:
+    if lib.hexo_gpu_abi_version() != 2:
         raise ImportError("libhexo_gpu.so has an unexpected ABI version; rebuild it")
     _lib = lib
     return lib

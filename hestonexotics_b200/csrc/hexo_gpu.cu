@@ -119,6 +119,31 @@ __global__ void shishua_streams_kernel(uint64_t seed0, uint64_t seed1_first, uin
   }
 }
 
+// K2b: Philox4x32-10 blocks (known-answer tests) and the words a stream hands to the stepper
+__global__ void philox_kernel(const uint32_t* ctr, const uint32_t* key, uint32_t* out, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t o[4];
+  philox4x32_10(ctr[4 * i], ctr[4 * i + 1], ctr[4 * i + 2], ctr[4 * i + 3], key[2 * i],
+                key[2 * i + 1], o);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) out[4 * i + j] = o[j];
+}
+__global__ void philox_streams_kernel(uint64_t seed, uint64_t first_stream, uint32_t n_streams,
+                                      uint64_t* out, size_t words_per_stream) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_streams) return;
+  PhiloxGen rng;
+  uint64_t o[16];
+  rng.init(seed, first_stream + i, 0, 0, o);
+  uint64_t* dst = out + (size_t)i * words_per_stream;
+  for (size_t off = 0; off < words_per_stream; off += 16) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) dst[off + j] = o[j];
+    rng.round(o);
+  }
+}
+
 // ---------------------------------------------------------------------------
 // K3: uniform map, inverse normal
 // ---------------------------------------------------------------------------
@@ -244,6 +269,8 @@ static int check_request(const hexo_price_request* r, bool need_strikes) {
     return fail(HEXO_ERR_INVALID_ARGUMENT, "unknown payoff %d", r->payoff);
   if (r->normal_mode != HEXO_NORMAL_F32 && r->normal_mode != HEXO_NORMAL_F64)
     return fail(HEXO_ERR_INVALID_ARGUMENT, "unknown normal_mode %d", r->normal_mode);
+  if (r->rng_mode != HEXO_RNG_SHISHUA && r->rng_mode != HEXO_RNG_PHILOX)
+    return fail(HEXO_ERR_INVALID_ARGUMENT, "unknown rng_mode %d", r->rng_mode);
   // The reference divides by kappa and sigma (HSimulation.tpp:60,75-77) and takes log(S) (:90);
   // it would silently produce NaN prices.  Refuse instead.
   const hexo_hparams& p = r->p;
@@ -309,7 +336,7 @@ static int build_segments(const hexo_price_request* r, bool with_strikes,
 // ---------------------------------------------------------------------------
 struct Plan {
   PathArgs args{};
-  int payoff = 0, normal_mode = 0;
+  int payoff = 0, normal_mode = 0, rng_mode = 0;
   uint32_t grid = 0, block = 0, smem = 0, n_opts = 0;
   uint64_t steps_per_path = 0, path_steps = 0, n_streams = 0;
   void* blob = nullptr;       // [segs | strikes | partials | sums]
@@ -328,7 +355,21 @@ static PathKernel pick_kernel_t(int payoff, int normal_mode) {
   return normal_mode == HEXO_NORMAL_F64 ? heston_qe_paths_kernel<HEXO_PAYOFF_EUROPEAN, 1, INL>
                                         : heston_qe_paths_kernel<HEXO_PAYOFF_EUROPEAN, 0, INL>;
 }
-static PathKernel pick_kernel(int payoff, int normal_mode, uint32_t n_seg) {
+// Philox mode: only the default kernel shape carries it (not the WS / IL experiments)
+template <bool INL>
+static PathKernel pick_philox_kernel_t(int payoff, int normal_mode) {
+  if (payoff == HEXO_PAYOFF_ASIAN)
+    return normal_mode == HEXO_NORMAL_F64
+               ? heston_qe_paths_kernel<HEXO_PAYOFF_ASIAN, 1, INL, PhiloxGen>
+               : heston_qe_paths_kernel<HEXO_PAYOFF_ASIAN, 0, INL, PhiloxGen>;
+  return normal_mode == HEXO_NORMAL_F64
+             ? heston_qe_paths_kernel<HEXO_PAYOFF_EUROPEAN, 1, INL, PhiloxGen>
+             : heston_qe_paths_kernel<HEXO_PAYOFF_EUROPEAN, 0, INL, PhiloxGen>;
+}
+static PathKernel pick_kernel(int payoff, int normal_mode, uint32_t n_seg, int rng_mode = 0) {
+  if (rng_mode == HEXO_RNG_PHILOX)
+    return n_seg <= (uint32_t)kInlineSegs ? pick_philox_kernel_t<true>(payoff, normal_mode)
+                                          : pick_philox_kernel_t<false>(payoff, normal_mode);
   return n_seg <= (uint32_t)kInlineSegs ? pick_kernel_t<true>(payoff, normal_mode)
                                         : pick_kernel_t<false>(payoff, normal_mode);
 }
@@ -404,11 +445,12 @@ static int plan_create(const hexo_price_request* r, uint64_t stream_begin, uint6
     const int b = atoi(e);
     if (b >= 32 && b <= kMaxBlock && b % 32 == 0) block = b;
   }
-  p->ws = use_ws();
+  p->rng_mode = r->rng_mode;
+  p->ws = r->rng_mode == HEXO_RNG_SHISHUA && use_ws();
   const size_t smem_budget = std::min(
       g_ctx.smem_optin, (size_t)(227 * 1024) / (p->ws ? kWsMinBlocks : kMinBlocksPerSM));
   if (p->ws) block = kWsBlock;
-  p->il = !p->ws && use_il();
+  p->il = r->rng_mode == HEXO_RNG_SHISHUA && !p->ws && use_il();
   const int streams_per_block = p->ws ? kWsConsumers : block;  // path-owning threads per block
   auto smem_of = [&](bool acc) {
     return p->ws   ? path_kernel_ws_smem(n_opts, r->normal_mode, acc)
@@ -473,7 +515,7 @@ static int plan_create(const hexo_price_request* r, uint64_t stream_begin, uint6
     HEXO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem));
   } else {
     PathKernel kern = p->il ? pick_il_kernel(p->payoff, p->normal_mode, p->args.n_seg)
-                            : pick_kernel(p->payoff, p->normal_mode, p->args.n_seg);
+                            : pick_kernel(p->payoff, p->normal_mode, p->args.n_seg, p->rng_mode);
     HEXO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem));
   }
   return HEXO_OK;
@@ -487,7 +529,7 @@ static int plan_launch(const Plan* p, cudaStream_t st, double* sums_out_dev) {
     kern<<<p->grid, p->block, p->smem, st>>>(p->args, (uint32_t)p->steps_per_path);
   } else {
     PathKernel kern = p->il ? pick_il_kernel(p->payoff, p->normal_mode, p->args.n_seg)
-                            : pick_kernel(p->payoff, p->normal_mode, p->args.n_seg);
+                            : pick_kernel(p->payoff, p->normal_mode, p->args.n_seg, p->rng_mode);
     kern<<<p->grid, p->block, p->smem, st>>>(p->args);
   }
   HEXO_CUDA(cudaGetLastError());
@@ -761,6 +803,45 @@ int hexo_gpu_shishua_streams(uint64_t seed, uint64_t first_stream, uint32_t n_st
   if (e == cudaSuccess) e = cudaMemcpy(bytes_out, d, total, cudaMemcpyDeviceToHost);
   cudaFree(d);
   if (e != cudaSuccess) return fail(HEXO_ERR_CUDA, "shishua kernel: %s", cudaGetErrorString(e));
+  return HEXO_OK;
+}
+
+int hexo_gpu_philox4x32(const uint32_t* counters, const uint32_t* keys, uint32_t* out, size_t n) {
+  if (!counters || !keys || !out || n == 0)
+    return fail(HEXO_ERR_INVALID_ARGUMENT, "philox: bad args");
+  int rc = ensure_context();
+  if (rc) return rc;
+  uint32_t *dc = nullptr, *dk = nullptr, *dout = nullptr;
+  HEXO_CUDA(cudaMalloc(&dc, n * 16));
+  HEXO_CUDA(cudaMalloc(&dk, n * 8));
+  HEXO_CUDA(cudaMalloc(&dout, n * 16));
+  cudaError_t e = cudaMemcpy(dc, counters, n * 16, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(dk, keys, n * 8, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    philox_kernel<<<(unsigned)((n + 127) / 128), 128>>>(dc, dk, dout, n);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpy(out, dout, n * 16, cudaMemcpyDeviceToHost);
+  cudaFree(dc); cudaFree(dk); cudaFree(dout);
+  if (e != cudaSuccess) return fail(HEXO_ERR_CUDA, "philox kernel: %s", cudaGetErrorString(e));
+  return HEXO_OK;
+}
+
+int hexo_gpu_philox_streams(uint64_t seed, uint64_t first_stream, uint32_t n_streams,
+                            uint64_t* words_out, size_t words_per_stream) {
+  if (!words_out || n_streams == 0 || words_per_stream == 0 || (words_per_stream & 15))
+    return fail(HEXO_ERR_INVALID_ARGUMENT, "philox: need a buffer and a multiple of 16 words");
+  int rc = ensure_context();
+  if (rc) return rc;
+  uint64_t* d = nullptr;
+  const size_t total = (size_t)n_streams * words_per_stream * 8;
+  HEXO_CUDA(cudaMalloc(&d, total));
+  philox_streams_kernel<<<(n_streams + 63) / 64, 64>>>(seed, first_stream, n_streams, d,
+                                                       words_per_stream);
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpy(words_out, d, total, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  if (e != cudaSuccess) return fail(HEXO_ERR_CUDA, "philox kernel: %s", cudaGetErrorString(e));
   return HEXO_OK;
 }
 

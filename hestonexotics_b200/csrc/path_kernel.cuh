@@ -26,6 +26,7 @@
 #include "../../include/hexo_gpu.h"
 #include "normals.cuh"
 #include "qe.cuh"
+#include "philox.cuh"
 #include "shishua.cuh"
 
 namespace hexo {
@@ -241,7 +242,7 @@ struct ZRing<HEXO_NORMAL_F64> {
   }
 };
 
-template <int PAYOFF, int NORMAL_MODE, bool INLINE_SEGS>
+template <int PAYOFF, int NORMAL_MODE, bool INLINE_SEGS, class Gen = Shishua>
 __global__ void __launch_bounds__(kMaxBlock, kMinBlocksPerSM)
 heston_qe_paths_kernel(const __grid_constant__ PathArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -278,7 +279,7 @@ heston_qe_paths_kernel(const __grid_constant__ PathArgs a) {
   // path counts are non-increasing in the stream id, so lane 0 holds the warp's maximum
   const uint64_t warp_paths = __shfl_sync(0xffffffffu, my_paths, 0);
 
-  Shishua rng;
+  Gen rng;  // Shishua (the reference's generator) or PhiloxGen (optional counter mode)
   auto refill = [&](uint64_t (&o)[16]) {
 #pragma unroll
     for (int s = 0; s < kStepsPerRound; ++s) {  // two 64-bit stores: a 128-bit store would need

@@ -40,6 +40,7 @@ class HQEAnderson:
 
 _NORMAL_MODES = {"f32": _lib.NORMAL_F32, "as-built": _lib.NORMAL_F32, "f64": _lib.NORMAL_F64,
                  _lib.NORMAL_F32: _lib.NORMAL_F32, _lib.NORMAL_F64: _lib.NORMAL_F64}
+_RNG_MODES = {"shishua": 0, "philox": 1, 0: 0, 1: 1}   # hexo_rng_mode
 
 
 @dataclass
@@ -61,7 +62,7 @@ class _Request:
 
     def __init__(self, scheme, p: HParams, S: float, all_chains: Sequence[OptionsChain],
                  n_simulations: int, n_opts: Optional[int], steps: int, seed: int, normal_mode,
-                 n_streams: int):
+                 n_streams: int, rng="shishua"):
         if isinstance(scheme, type) and hasattr(scheme, "payoff"):
             scheme = HQEAnderson(scheme)
         self.expiries, self.offsets, self.strikes = flatten_chains(all_chains)
@@ -71,12 +72,15 @@ class _Request:
             raise ValueError(f"n_opts={n_opts} but the chains hold {self.n_opts} options")
         if normal_mode not in _NORMAL_MODES:
             raise ValueError(f"normal_mode must be 'f32' or 'f64', got {normal_mode!r}")
+        if rng not in _RNG_MODES:
+            raise ValueError(f"rng must be 'shishua' or 'philox', got {rng!r}")
         self.req = _lib.HexoPriceRequest(
             _lib.HexoHParams(*p.as_tuple()), float(S), scheme.payoff, len(self.expiries),
             self.expiries.ctypes.data_as(_lib.c_double_p),
             self.offsets.ctypes.data_as(_lib.c_uint32_p),
             self.strikes.ctypes.data_as(_lib.c_double_p),
-            int(n_simulations), int(steps), int(seed), _NORMAL_MODES[normal_mode], int(n_streams))
+            int(n_simulations), int(steps), int(seed), _NORMAL_MODES[normal_mode],
+            _RNG_MODES[rng], int(n_streams))
 
 
 def _finish(sums: np.ndarray, n_paths: int, n_opts: int):
@@ -91,12 +95,14 @@ def _finish(sums: np.ndarray, n_paths: int, n_opts: int):
 
 def price_full(scheme, p: HParams, S: float, all_chains: Sequence[OptionsChain],
                n_simulations: int, n_opts: Optional[int], steps: int, *, seed: int = 1,
-               normal_mode="f32", n_streams: int = 0, device: Optional[int] = None) -> PriceResult:
+               normal_mode="f32", n_streams: int = 0, rng="shishua",
+               device: Optional[int] = None) -> PriceResult:
     """price<Scheme>() on one GPU, returning prices, standard errors and launch statistics."""
     lib = _lib.load()
     if device is not None:
         _lib.check(lib.hexo_gpu_init(int(device)))
-    rq = _Request(scheme, p, S, all_chains, n_simulations, n_opts, steps, seed, normal_mode, n_streams)
+    rq = _Request(scheme, p, S, all_chains, n_simulations, n_opts, steps, seed, normal_mode,
+                  n_streams, rng)
     if rq.req.n_streams == 0:
         rq.req.n_streams = lib.hexo_gpu_default_streams(rq.req.n_paths, rq.n_opts, 1)
     sums = np.zeros(2 * rq.n_opts, dtype=np.float64)
@@ -111,11 +117,12 @@ def price_full(scheme, p: HParams, S: float, all_chains: Sequence[OptionsChain],
 
 def price_multi(scheme, p: HParams, S: float, all_chains: Sequence[OptionsChain],
                 n_simulations: int, n_opts: Optional[int], steps: int, *, n_gpus: int = 0,
-                seed: int = 1, normal_mode="f32", n_streams: int = 0):
+                seed: int = 1, normal_mode="f32", n_streams: int = 0, rng="shishua"):
     """price<Scheme>() spread over several GPUs of THIS process (hexo_gpu_price_multi); returns
     (prices, stderr).  n_gpus = 0 uses every visible device."""
     lib = _lib.load()
-    rq = _Request(scheme, p, S, all_chains, n_simulations, n_opts, steps, seed, normal_mode, n_streams)
+    rq = _Request(scheme, p, S, all_chains, n_simulations, n_opts, steps, seed, normal_mode,
+                  n_streams, rng)
     prices, se = np.zeros(rq.n_opts), np.zeros(rq.n_opts)
     _lib.check(lib.hexo_gpu_price_multi(C.byref(rq.req), int(n_gpus),
                                         prices.ctypes.data_as(_lib.c_double_p),
@@ -138,7 +145,7 @@ def shard_range(n_streams: int, rank: int, world_size: int):
 
 def price_distributed(scheme, p: HParams, S: float, all_chains: Sequence[OptionsChain],
                       n_simulations: int, n_opts: Optional[int], steps: int, *, seed: int = 1,
-                      normal_mode="f32", n_streams: int = 0, group=None,
+                      normal_mode="f32", n_streams: int = 0, rng="shishua", group=None,
                       _shard_sums=None) -> PriceResult:
     """price<Scheme>() sharded over the ranks of a torch.distributed group.
 
@@ -152,7 +159,8 @@ def price_distributed(scheme, p: HParams, S: float, all_chains: Sequence[Options
     import torch.distributed as dist
 
     rank, world = dist.get_rank(group), dist.get_world_size(group)
-    rq = _Request(scheme, p, S, all_chains, n_simulations, n_opts, steps, seed, normal_mode, n_streams)
+    rq = _Request(scheme, p, S, all_chains, n_simulations, n_opts, steps, seed, normal_mode,
+                  n_streams, rng)
     stats = _lib.HexoGpuStats()
     if _shard_sums is None:
         lib = _lib.load()

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define HEXO_GPU_ABI_VERSION 1
+#define HEXO_GPU_ABI_VERSION 2 /* 2: rng_mode in hexo_price_request (former padding) */
 
 typedef enum {
   HEXO_OK = 0,
@@ -50,6 +50,12 @@ typedef enum { HEXO_PAYOFF_ASIAN = 0, HEXO_PAYOFF_EUROPEAN = 1 } hexo_payoff;
  * and nothing in Makefile.am promotes them.  F64 is the documented AS241
  * accuracy ("1 part in 10**16", as241.f90:4). */
 typedef enum { HEXO_NORMAL_F32 = 0, HEXO_NORMAL_F64 = 1 } hexo_normal_mode;
+
+/* Generator of the u64 words.  SHISHUA is the reference's (src/RNG.cpp:24-29, stream s seeded
+ * {seed,s,0,0}).  PHILOX is an optional counter-based mode that the reference does not have:
+ * the n-th stepper call of stream s draws Philox4x32-10(counter {n_lo,n_hi,s_lo,s_hi}, key
+ * {seed_lo,seed_hi}) = (c0..c3); variance word c0|c1<<32, spot word c2|c3<<32. */
+typedef enum { HEXO_RNG_SHISHUA = 0, HEXO_RNG_PHILOX = 1 } hexo_rng_mode;
 
 /* HParams, src/inc/HDistribution.h:9-24 -- same field order, same meaning */
 typedef struct {
@@ -77,6 +83,7 @@ typedef struct {
   uint32_t steps;                 /* `steps`: step width = expiry/steps         */
   uint64_t seed;                  /* stream s is shishua seeded {seed,s,0,0}    */
   int32_t normal_mode;            /* hexo_normal_mode                           */
+  int32_t rng_mode;               /* hexo_rng_mode; 0 = the reference's shishua */
   uint64_t n_streams;             /* independent RNG streams the n_paths are    */
                                   /* split over; 0 = pick for the device(s).    */
                                   /* For a fixed (seed,n_paths,n_streams) the   */
@@ -169,6 +176,13 @@ int hexo_gpu_shishua_fill(const uint64_t seed[4], uint8_t *bytes_out, size_t n_b
  * bytes_out[i*bytes_per_stream ...] (bytes_per_stream multiple of 128) */
 int hexo_gpu_shishua_streams(uint64_t seed, uint64_t first_stream, uint32_t n_streams,
                              uint8_t *bytes_out, size_t bytes_per_stream);
+
+/* Optional Philox mode (hexo_rng_mode): n Philox4x32-10 blocks, counters[4n], keys[2n] ->
+ * out[4n] (Random123 known-answer vectors), and the first `words_per_stream` (multiple of 16)
+ * u64 words streams [first_stream, first_stream+n_streams) hand to the stepper. */
+int hexo_gpu_philox4x32(const uint32_t *counters, const uint32_t *keys, uint32_t *out, size_t n);
+int hexo_gpu_philox_streams(uint64_t seed, uint64_t first_stream, uint32_t n_streams,
+                            uint64_t *words_out, size_t words_per_stream);
 
 /* ---- K3: uniform map and inverse normal (RNG.cpp:31, as241.f90:15-119) ------ */
 int hexo_gpu_u64_to_unit(const uint64_t *bits_in, double *u_out, size_t n);

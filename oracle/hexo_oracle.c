@@ -203,6 +203,22 @@ static double refsrc_g(draw_src *d) { return oracle_rng_grand((oracle_rng *)d->c
 static double refsrc_u(draw_src *d) { return oracle_rng_urand((oracle_rng *)d->ctx); }
 static void refsrc_end(draw_src *d) { (void)d; }
 
+void oracle_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+  uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3], k0 = key[0], k1 = key[1];
+  for (int r = 0; r < 10; ++r) {
+    const uint64_t p0 = (uint64_t)M0 * c0, p1 = (uint64_t)M1 * c2;
+    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+    c1 = (uint32_t)p1;
+    c3 = (uint32_t)p0;
+    c0 = n0;
+    c2 = n2;
+    k0 += W0;
+    k1 += W1;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
 /* (b) GPU stream convention: two consecutive u64 words per step */
 typedef struct {
   prng_state s;
@@ -211,10 +227,24 @@ typedef struct {
   int normal_mode;
   uint64_t w_var, w_spot;
   int have;
+  int rng_mode;          /* 0 shishua, 1 philox */
+  uint64_t seed, stream, n_step;
 } stream_ctx;
 
 static void stream_fetch(stream_ctx *c) {
   if (c->have) return;
+  if (c->rng_mode == 1) {
+    const uint32_t ctr[4] = {(uint32_t)c->n_step, (uint32_t)(c->n_step >> 32), (uint32_t)c->stream,
+                             (uint32_t)(c->stream >> 32)};
+    const uint32_t key[2] = {(uint32_t)c->seed, (uint32_t)(c->seed >> 32)};
+    uint32_t o[4];
+    oracle_philox4x32_10(ctr, key, o);
+    c->w_var = (uint64_t)o[0] | ((uint64_t)o[1] << 32);
+    c->w_spot = (uint64_t)o[2] | ((uint64_t)o[3] << 32);
+    c->n_step++;
+    c->have = 1;
+    return;
+  }
   if (c->pos == 16) {
     prng_gen(&c->s, (uint8_t *)c->block, 128);
     c->pos = 0;
@@ -460,6 +490,13 @@ int oracle_price_ref(const oracle_contract *c, unsigned int n_sims, unsigned int
 int oracle_price_stream(const oracle_contract *c, uint64_t seed, uint64_t n_paths,
                         uint64_t n_streams_total, uint64_t stream_begin, uint64_t stream_count,
                         int normal_mode, double *sum, double *sumsq) {
+  return oracle_price_stream_rng(c, 0, seed, n_paths, n_streams_total, stream_begin, stream_count,
+                                 normal_mode, sum, sumsq);
+}
+
+int oracle_price_stream_rng(const oracle_contract *c, int rng_mode, uint64_t seed, uint64_t n_paths,
+                            uint64_t n_streams_total, uint64_t stream_begin, uint64_t stream_count,
+                            int normal_mode, double *sum, double *sumsq) {
   int rc = check_contract(c);
   if (rc) return rc;
   if (n_streams_total == 0 || stream_begin + stream_count > n_streams_total) return -1;
@@ -475,6 +512,10 @@ int oracle_price_stream(const oracle_contract *c, uint64_t seed, uint64_t n_path
     prng_init(&sc.s, sd);
     sc.pos = 16;
     sc.normal_mode = normal_mode;
+    sc.rng_mode = rng_mode;
+    sc.seed = seed;
+    sc.stream = s;
+    sc.n_step = 0;
     draw_src d = {strsrc_gv, strsrc_uv, strsrc_gx, strsrc_end, &sc};
     const uint64_t my_paths = base + (s < rem ? 1 : 0);
     for (uint64_t i = 0; i < my_paths; ++i) simulate_path(c, &d, 0, pay_sums, &sink);

@@ -89,6 +89,16 @@ int oracle_price_stream(const oracle_contract *c, uint64_t seed, uint64_t n_path
                         uint64_t n_streams_total, uint64_t stream_begin, uint64_t stream_count,
                         int normal_mode, double *sum, double *sumsq);
 
+/* Philox4x32-10 (Salmon et al., SC'11): optional generator of the GPU path, not in the reference */
+void oracle_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+
+/* oracle_price_stream with a choice of generator: rng_mode 0 = shishua (as above), 1 = Philox:
+ * the n-th stepper call of stream s uses Philox4x32-10(counter {n_lo,n_hi,s_lo,s_hi}, key
+ * {seed_lo,seed_hi}); variance word = c0|c1<<32, spot word = c2|c3<<32. */
+int oracle_price_stream_rng(const oracle_contract *c, int rng_mode, uint64_t seed, uint64_t n_paths,
+                            uint64_t n_streams_total, uint64_t stream_begin, uint64_t stream_count,
+                            int normal_mode, double *sum, double *sumsq);
+
 /* ---- tape replay ------------------------------------------------------------
  * tape[path][step][3] = {Z_V, U_V, Z_X}; the stepper takes Z_V or U_V according
  * to its branch.  finals[path][chain] receives the policy's final_value (Asian

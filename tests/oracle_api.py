@@ -70,6 +70,11 @@ def oracle() -> C.CDLL:
                                        C.c_int, dp, dp, dp]
         o.oracle_price_stream.argtypes = [C.POINTER(OracleContract), C.c_uint64, C.c_uint64,
                                           C.c_uint64, C.c_uint64, C.c_uint64, C.c_int, dp, dp]
+        o.oracle_price_stream_rng.argtypes = [C.POINTER(OracleContract), C.c_int, C.c_uint64,
+                                              C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64,
+                                              C.c_int, dp, dp]
+        o.oracle_philox4x32_10.argtypes = [C.POINTER(C.c_uint32)] * 3
+        o.oracle_philox4x32_10.restype = None
         o.oracle_replay.argtypes = [C.POINTER(OracleContract), dp, C.c_uint64, C.c_uint32, dp]
         o.oracle_steps_to_last_expiry.restype = C.c_uint32
         o.oracle_steps_to_last_expiry.argtypes = [C.POINTER(OracleContract)]
@@ -128,11 +133,12 @@ class Contract:
         return pr, sm, sq
 
     def price_stream(self, seed, n_paths, n_streams, begin=0, count=None,
-                     normal_mode=NORMAL_F32):
+                     normal_mode=NORMAL_F32, rng_mode=0):
         count = n_streams - begin if count is None else count
         sm, sq = np.zeros(self.n_opts), np.zeros(self.n_opts)
-        rc = oracle().oracle_price_stream(C.byref(self.c), seed, n_paths, n_streams, begin, count,
-                                          normal_mode, sm.ctypes.data_as(dp), sq.ctypes.data_as(dp))
+        rc = oracle().oracle_price_stream_rng(C.byref(self.c), rng_mode, seed, n_paths, n_streams,
+                                              begin, count, normal_mode, sm.ctypes.data_as(dp),
+                                              sq.ctypes.data_as(dp))
         assert rc == 0, rc
         return sm, sq
 

@@ -12,10 +12,10 @@ _lib.check(lib.hexo_gpu_measure_fp64_peak(C.byref(fl), C.byref(ms)))
 print(f"fp64 DFMA peak: {fl.value/1e12:.2f} TFLOP/s ({ms.value:.2f} ms)")
 p = hx.HParams(0.04, 0.04, -0.7, 2.0, 0.5)
 A = hx.HQEAnderson(hx.AAsianCallNonAdaptive); E = hx.HQEAnderson(hx.EuropeanCallNonAdaptive)
-def run(name, scheme, T, K, n, steps, mode, p=p):
+def run(name, scheme, T, K, n, steps, mode, p=p, rng="shishua"):
     ch = [hx.OptionsChain.from_strikes(t, k) for t, k in zip(T, K)]
-    r = hx.price_full(scheme, p, 100.0, ch, n, None, steps, seed=1, normal_mode=mode)
-    r = hx.price_full(scheme, p, 100.0, ch, n, None, steps, seed=2, normal_mode=mode)
+    r = hx.price_full(scheme, p, 100.0, ch, n, None, steps, seed=1, normal_mode=mode, rng=rng)
+    r = hx.price_full(scheme, p, 100.0, ch, n, None, steps, seed=2, normal_mode=mode, rng=rng)
     print(f"{name:28s} {mode} n={n:.1e} steps={steps} ms={r.kernel_ms:9.2f} rate={r.path_steps/r.kernel_ms/1e6:8.2f} Gps/s grid={r.grid}x{r.block} price0={r.prices[0]:.4f}+-{r.stderr[0]:.4f}", flush=True)
 scale = float(sys.argv[1]) if len(sys.argv) > 1 else 1.0
 for mode in ("f32", "f64"):
@@ -24,3 +24,5 @@ for mode in ("f32", "f64"):
     run("cfg4 asian 1024", A, [1.0], [[100.0]], int(2e7*scale), 1024, mode)
     run("cfg3 chain 64x8", A, [0.25*k for k in range(1,9)], [list(np.linspace(70,130,64))]*8, int(2e6*scale), 252, mode)
     run("cfg5 stiff", A, [10.0], [list(np.linspace(70,130,64))], int(2e6*scale), 2520, mode, hx.HParams(0.04,0.04,-0.95,20.0,1.0))
+run("cfg4 asian 1024 PHILOX", A, [1.0], [[100.0]], int(2e7*scale), 1024, "f32", rng="philox")
+run("cfg2 euro 1M PHILOX", E, [1.0], [[100.0]], 1_000_000, 252, "f32", rng="philox")
