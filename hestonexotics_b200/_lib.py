@@ -20,7 +20,7 @@ ABI_SYMBOLS = (
     "hexo_gpu_shishua_streams", "hexo_gpu_u64_to_unit", "hexo_gpu_ppnd16", "hexo_gpu_replay",
     "hexo_gpu_measure_fp64_peak", "hexo_gpu_plan_create", "hexo_gpu_plan_launch",
     "hexo_gpu_plan_sums_device", "hexo_gpu_plan_stats", "hexo_gpu_plan_destroy",
-    "hexo_gpu_philox4x32", "hexo_gpu_philox_streams",
+    "hexo_gpu_philox4x32", "hexo_gpu_philox_streams", "hexo_gpu_price_batch",
 )
 # host-only semi-analytic benchmark functions of the same library (no hexo_gpu_ prefix)
 HOST_SYMBOLS = ("hexo_heston_chf", "hexo_swift_default_params", "hexo_swift_price_chain")
@@ -112,6 +112,8 @@ def load() -> C.CDLL:
     lib.hexo_gpu_shishua_fill.argtypes = [c_uint64_p, c_uint8_p, C.c_size_t]
     lib.hexo_gpu_shishua_streams.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, c_uint8_p,
                                              C.c_size_t]
+    lib.hexo_gpu_price_batch.argtypes = [C.POINTER(HexoPriceRequest), C.c_uint32, C.c_uint32,
+                                         c_double_p, c_double_p, C.POINTER(HexoGpuStats)]
     lib.hexo_gpu_philox4x32.argtypes = [c_uint32_p, c_uint32_p, c_uint32_p, C.c_size_t]
     lib.hexo_gpu_philox_streams.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, c_uint64_p,
                                             C.c_size_t]

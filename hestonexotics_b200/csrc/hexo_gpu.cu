@@ -710,6 +710,93 @@ int hexo_gpu_price(const hexo_price_request* req, double* prices_out, double* st
   return HEXO_OK;
 }
 
+// Many independent price<>() calls in one submission (Monte-Carlo inside a
+// calibration loop prices the same chains for many HParams).  Request i runs on CUDA stream
+// i % n_lanes of the current device, so launches, the tail of one job and the head of the next
+// overlap; every job computes exactly what hexo_gpu_price computes for it (same streams, same
+// sums).  One device-to-host copy of all sums at the end.
+int hexo_gpu_price_batch(const hexo_price_request* reqs, uint32_t n_reqs, uint32_t n_lanes,
+                         double* prices_out, double* stderr_out, hexo_gpu_stats* stats) {
+  if (!reqs || n_reqs == 0) return fail(HEXO_ERR_INVALID_ARGUMENT, "empty batch");
+  if (!prices_out) return fail(HEXO_ERR_INVALID_ARGUMENT, "prices_out is NULL");
+  std::vector<size_t> off(n_reqs + 1, 0);
+  for (uint32_t i = 0; i < n_reqs; ++i) {
+    const int rc = check_request(&reqs[i], true);
+    if (rc) return rc;
+    off[i + 1] = off[i] + 2 * (size_t)reqs[i].strike_offsets[reqs[i].n_chains];
+  }
+  int rc = ensure_context();
+  if (rc) return rc;
+  if (n_lanes == 0) n_lanes = 16;
+  n_lanes = std::min(n_lanes, std::min<uint32_t>(n_reqs, 32));
+  std::vector<cudaStream_t> lanes(n_lanes, nullptr);
+  std::vector<cudaEvent_t> done(n_lanes, nullptr);
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  double* all_sums = nullptr;
+  std::vector<Plan> plans(n_reqs);
+  std::vector<double> sums(off[n_reqs]);
+  float ms = 0.f;
+  auto cleanup = [&]() {
+    for (auto st : lanes)
+      if (st) cudaStreamDestroy(st);
+    for (auto ev : done)
+      if (ev) cudaEventDestroy(ev);
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    if (all_sums) cudaFree(all_sums);
+  };
+  cudaError_t e = cudaMalloc(&all_sums, off[n_reqs] * sizeof(double));
+  for (uint32_t l = 0; l < n_lanes && e == cudaSuccess; ++l) {
+    e = cudaStreamCreateWithFlags(&lanes[l], cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&done[l], cudaEventDisableTiming);
+  }
+  if (e == cudaSuccess) e = cudaEventCreate(&e0);
+  if (e == cudaSuccess) e = cudaEventCreate(&e1);
+  if (e != cudaSuccess) {
+    cleanup();
+    return fail(HEXO_ERR_CUDA, "batch setup: %s", cudaGetErrorString(e));
+  }
+  cudaEventRecord(e0, lanes[0]);
+  for (uint32_t l = 1; l < n_lanes; ++l) cudaStreamWaitEvent(lanes[l], e0, 0);
+  for (uint32_t i = 0; i < n_reqs && rc == HEXO_OK; ++i) {
+    cudaStream_t st = lanes[i % n_lanes];
+    hexo_price_request r = reqs[i];
+    if (r.n_streams == 0) r.n_streams = default_streams(r.n_paths, 1);
+    rc = plan_create(&r, 0, r.n_streams, st, &plans[i]);
+    if (rc) break;
+    rc = plan_launch(&plans[i], st, all_sums + off[i]);
+    plan_destroy(&plans[i], st);  // stream-ordered: freed after the job's kernels
+  }
+  for (uint32_t l = 1; l < n_lanes; ++l) {
+    cudaEventRecord(done[l], lanes[l]);
+    cudaStreamWaitEvent(lanes[0], done[l], 0);
+  }
+  cudaEventRecord(e1, lanes[0]);
+  e = cudaStreamSynchronize(lanes[0]);
+  for (uint32_t l = 1; l < n_lanes; ++l) cudaStreamSynchronize(lanes[l]);
+  if (rc == HEXO_OK && e == cudaSuccess)
+    e = cudaMemcpy(sums.data(), all_sums, sums.size() * sizeof(double), cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess) cudaEventElapsedTime(&ms, e0, e1);
+  cleanup();
+  if (rc) return rc;
+  if (e != cudaSuccess) return fail(HEXO_ERR_CUDA, "batch: %s", cudaGetErrorString(e));
+  for (uint32_t i = 0; i < n_reqs; ++i) {
+    const uint32_t n_opts = (uint32_t)((off[i + 1] - off[i]) / 2);
+    const double* sm = sums.data() + off[i];
+    const double n = (double)reqs[i].n_paths;
+    for (uint32_t j = 0; j < n_opts; ++j) {
+      const double mean = sm[j] / n;  // HSimulation.tpp:40
+      prices_out[off[i] / 2 + j] = mean;
+      if (stderr_out) {
+        const double var = n > 1 ? std::max(0.0, (sm[n_opts + j] - n * mean * mean) / (n - 1)) : 0.0;
+        stderr_out[off[i] / 2 + j] = sqrt(var / n);
+      }
+    }
+    if (stats) fill_stats(plans[i], ms, &stats[i]);  // kernel_ms = the whole batch
+  }
+  return HEXO_OK;
+}
+
 // One process, several GPUs: the single-process form of the multi-GPU path for callers like the
 // reference's CLI, which is one process.  Streams are split over the first n_gpus devices
 // exactly like hx.price_distributed splits them over ranks; the 2*n_opts sums of each device come

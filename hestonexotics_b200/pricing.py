@@ -130,6 +130,32 @@ def price_multi(scheme, p: HParams, S: float, all_chains: Sequence[OptionsChain]
     return prices, se
 
 
+def price_batch(scheme, params: Sequence[HParams], S: float, all_chains: Sequence[OptionsChain],
+                n_simulations: int, n_opts: Optional[int], steps: int, *, seeds=1,
+                normal_mode="f32", n_streams: int = 0, rng="shishua", n_lanes: int = 0):
+    """price<Scheme>() of the same chains for MANY parameter sets in one submission
+    (hexo_gpu_price_batch): the shape of Monte-Carlo pricing inside a calibration loop.  `seeds`
+    is one seed for all jobs (common random numbers) or one per parameter set.  Returns
+    (prices[n_params, n_opts], stderr[n_params, n_opts], batch_ms)."""
+    lib = _lib.load()
+    params = list(params)
+    if not params:
+        raise ValueError("price_batch needs at least one parameter set")
+    seeds = [int(seeds)] * len(params) if np.isscalar(seeds) else [int(x) for x in seeds]
+    if len(seeds) != len(params):
+        raise ValueError("one seed per parameter set")
+    rqs = [_Request(scheme, p, S, all_chains, n_simulations, n_opts, steps, sd, normal_mode,
+                    n_streams, rng) for p, sd in zip(params, seeds)]
+    arr = (_lib.HexoPriceRequest * len(rqs))(*[r.req for r in rqs])
+    n = rqs[0].n_opts
+    prices, se = np.zeros((len(rqs), n)), np.zeros((len(rqs), n))
+    stats = (_lib.HexoGpuStats * len(rqs))()
+    _lib.check(lib.hexo_gpu_price_batch(arr, len(rqs), int(n_lanes),
+                                        prices.ctypes.data_as(_lib.c_double_p),
+                                        se.ctypes.data_as(_lib.c_double_p), stats))
+    return prices, se, float(stats[0].kernel_ms)
+
+
 def price(scheme, p: HParams, S: float, all_chains: Sequence[OptionsChain], n_simulations: int,
           n_opts: Optional[int], steps: int, **kw) -> np.ndarray:
     """Drop-in for HSimulation::price<Scheme>: returns the n_opts prices, chain-major."""

@@ -131,6 +131,15 @@ int hexo_gpu_schedule(const double *expiries, uint32_t n_chains, uint32_t steps,
 int hexo_gpu_price(const hexo_price_request *req, double *prices_out, double *stderr_out,
                    hexo_gpu_stats *stats);
 
+/* n_reqs independent price<>() calls in one submission -- the shape of Monte-Carlo pricing
+ * inside a calibration loop (src/Main.cpp:88 evaluated for many HParams).  Request i runs on CUDA
+ * stream i % n_lanes (0 = 16 lanes) of the current device so that small jobs overlap; each job's
+ * result is exactly hexo_gpu_price's for the same request.  prices_out / stderr_out (or NULL)
+ * are request-major: request i's n_opts values follow request i-1's.  stats (or NULL) is
+ * [n_reqs]; kernel_ms there is the device time of the whole batch. */
+int hexo_gpu_price_batch(const hexo_price_request *reqs, uint32_t n_reqs, uint32_t n_lanes,
+                         double *prices_out, double *stderr_out, hexo_gpu_stats *stats);
+
 /* The same call spread over the first n_gpus devices of this process (n_gpus <= 0: all
  * visible devices): the single-process counterpart of the one-rank-per-GPU path, for callers
  * like the reference's CLI.  Streams are split over devices like ranks split them; the sums

@@ -385,3 +385,90 @@ def test_very_wide_chain_uses_device_accumulators(gpu):
                       normal_mode="f64", n_streams=64)
     assert np.allclose(r.sums[:20000], sm, rtol=1e-10, atol=1e-9)
     assert np.allclose(r.sums[20000:], sq, rtol=1e-10, atol=1e-9)
+
+
+# ---- randomised contracts ---------------------------------------------------------
+
+def _random_contract(rng):
+    payoff = int(rng.integers(0, 2))
+    n_chains = int(rng.integers(1, 5))
+    T = np.cumsum(rng.uniform(0.02, 0.9, size=n_chains)).tolist()
+    S = float(rng.uniform(20.0, 400.0))
+    K = [sorted((S * rng.uniform(0.6, 1.4, size=int(rng.integers(1, 6)))).tolist())
+         for _ in range(n_chains)]
+    steps = int(rng.integers(1, 90))
+    params = (float(rng.uniform(0.005, 0.2)), float(rng.uniform(0.005, 0.2)),
+              float(rng.uniform(-0.95, 0.5)), float(rng.uniform(0.2, 8.0)),
+              float(rng.uniform(0.05, 1.5)))   # Feller condition violated in about half the draws
+    n_paths = int(rng.integers(1, 1500))
+    n_streams = int(rng.integers(1, min(n_paths, 300) + 1))
+    return payoff, T, K, steps, params, S, n_paths, n_streams
+
+
+@pytest.mark.parametrize("i", range(24))
+def test_random_contracts_sums_vs_oracle(gpu, i):
+    """Seeded random contracts (maturities, ragged strike chains, step counts, parameters, spot,
+    path / stream counts, generator): the fused kernel's payoff sums equal the oracle's."""
+    rng = np.random.default_rng(1000 + i)
+    payoff, T, K, steps, params, S, n_paths, n_streams = _random_contract(rng)
+    rng_mode = i % 2
+    seed = int(rng.integers(0, 2 ** 63))
+    c = oa.Contract(payoff, T, K, steps, params, S)
+    sm, sq = c.price_stream(seed, n_paths, n_streams, normal_mode=oa.NORMAL_F64, rng_mode=rng_mode)
+    res = hx.price_full(ASIAN if payoff == oa.ASIAN else EURO, hx.HParams(*params), S,
+                        chains_of(T, K), n_paths, c.n_opts, steps, seed=seed, normal_mode="f64",
+                        n_streams=n_streams, rng=("shishua", "philox")[rng_mode])
+    n = c.n_opts
+    # absolute floor: a sum of n_paths payoffs of size ~S carries rounding of ~n_paths*S*eps
+    floor = 1e-12 * n_paths * S
+    assert np.all(np.abs(res.sums[:n] - sm) <= 1e-10 * np.abs(sm) + floor)
+    assert np.all(np.abs(res.sums[n:] - sq) <= 2e-10 * np.abs(sq) + floor * S)
+    assert res.steps_per_path == c.steps_to_last_expiry()
+
+
+# ---- batched submission -------------------------------------------------------------
+
+def test_price_batch_equals_single_calls(gpu):
+    """hexo_gpu_price_batch: every job's prices are bit-identical to hexo_gpu_price's."""
+    rng = np.random.default_rng(77)
+    params = [hx.HParams(float(rng.uniform(0.01, 0.1)), float(rng.uniform(0.01, 0.1)),
+                         float(rng.uniform(-0.9, 0.0)), float(rng.uniform(0.5, 5.0)),
+                         float(rng.uniform(0.1, 1.0))) for _ in range(13)]
+    chains = chains_of([0.5, 1.0], [[90.0, 100.0], [95.0, 100.0, 110.0]])
+    seeds = [int(x) for x in rng.integers(1, 2 ** 40, size=len(params))]
+    for lanes in (0, 1, 3):
+        pr, se, ms = hx.price_batch(ASIAN, params, 100.0, chains, 20_000, 5, 40, seeds=seeds,
+                                    n_streams=1000, n_lanes=lanes)
+        assert pr.shape == (13, 5) and ms > 0
+        for i, (p, sd) in enumerate(zip(params, seeds)):
+            one = hx.price_full(ASIAN, p, 100.0, chains, 20_000, 5, 40, seed=sd, n_streams=1000)
+            assert np.array_equal(pr[i], one.prices)
+            assert np.array_equal(se[i], one.stderr)
+
+
+def test_price_batch_mixed_requests_and_errors(gpu):
+    """Different contracts in one batch through the C ABI; a bad request fails the whole batch."""
+    from hestonexotics_b200 import pricing
+    p = hx.HParams(*oa.DEFAULT_PARAMS)
+    jobs = [(ASIAN, chains_of([1.0], [[100.0]]), 5000, 32, "f32", "shishua"),
+            (EURO, chains_of([0.25, 0.5], [[90.0, 110.0], [100.0]]), 7000, 20, "f64", "philox"),
+            (ASIAN, chains_of([2.0], [list(np.linspace(80, 120, 40))]), 3000, 64, "f64", "shishua")]
+    rqs = [pricing._Request(s, p, 100.0, ch, n, None, st, 5, nm, 500, rg)
+           for s, ch, n, st, nm, rg in jobs]
+    arr = (_lib.HexoPriceRequest * len(rqs))(*[r.req for r in rqs])
+    total = sum(r.n_opts for r in rqs)
+    prices, se = np.zeros(total), np.zeros(total)
+    rc = gpu.hexo_gpu_price_batch(arr, len(rqs), 2, prices.ctypes.data_as(_lib.c_double_p),
+                                  se.ctypes.data_as(_lib.c_double_p), None)
+    assert rc == 0
+    o = 0
+    for (s, ch, n, st, nm, rg), r in zip(jobs, rqs):
+        one = hx.price_full(s, p, 100.0, ch, n, None, st, seed=5, normal_mode=nm, n_streams=500,
+                            rng=rg)
+        assert np.array_equal(prices[o:o + r.n_opts], one.prices)
+        o += r.n_opts
+    arr[1].steps = 0
+    assert gpu.hexo_gpu_price_batch(arr, len(rqs), 2, prices.ctypes.data_as(_lib.c_double_p),
+                                    None, None) == -1
+    assert gpu.hexo_gpu_price_batch(arr, 0, 2, prices.ctypes.data_as(_lib.c_double_p),
+                                    None, None) == -1

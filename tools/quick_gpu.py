@@ -26,3 +26,20 @@ for mode in ("f32", "f64"):
     run("cfg5 stiff", A, [10.0], [list(np.linspace(70,130,64))], int(2e6*scale), 2520, mode, hx.HParams(0.04,0.04,-0.95,20.0,1.0))
 run("cfg4 asian 1024 PHILOX", A, [1.0], [[100.0]], int(2e7*scale), 1024, "f32", rng="philox")
 run("cfg2 euro 1M PHILOX", E, [1.0], [[100.0]], 1_000_000, 252, "f32", rng="philox")
+# batched submission: cfg1-sized jobs (10^5 paths x 252 steps) for 64 parameter sets
+import time
+ps = [hx.HParams(0.04 + 0.0005 * i, 0.04, -0.7, 2.0, 0.5) for i in range(64)]
+ch1 = [hx.OptionsChain.from_strikes(1.0, [100.0])]
+for _ in range(2):
+    t0 = time.perf_counter()
+    for q in ps:
+        hx.price_full(A, q, 100.0, ch1, 100_000, None, 252)
+    t_seq = time.perf_counter() - t0
+for lanes in (1, 2, 4, 8, 16):
+    for _ in range(2):
+        t0 = time.perf_counter()
+        pr, se, ms = hx.price_batch(A, ps, 100.0, ch1, 100_000, None, 252, n_lanes=lanes)
+        t_b = time.perf_counter() - t0
+    print(f"batch 64 x cfg1: lanes={lanes:2d} device {ms:7.2f} ms  host {t_b*1e3:7.2f} ms  "
+          f"({64*100_000*252/t_b/1e9:6.1f} Gps/s)   sequential price_full {t_seq*1e3:7.2f} ms "
+          f"({64*100_000*252/t_seq/1e9:6.1f} Gps/s)", flush=True)
