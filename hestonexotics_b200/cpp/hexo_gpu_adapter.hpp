@@ -45,6 +45,7 @@ struct GpuPriceOptions {
   uint64_t seed = 1;                      // the reference's thread-0 seed (HSimulation.tpp:28)
   int normal_mode = HEXO_NORMAL_F32;      // the reference as built (as241.f90:20-25)
   int rng_mode = HEXO_RNG_SHISHUA;        // the reference's generator; HEXO_RNG_PHILOX optional
+  int schedule_mode = HEXO_SCHEDULE_REFERENCE;  // the reference's time grid, quirks included
   uint64_t n_streams = 0;                 // 0 = sized for the device(s)
   int n_gpus = 1;                         // devices of this process to spread over; 0 = all
   std::vector<ffloat>* stderr_out = nullptr;  // optional Monte-Carlo standard errors
@@ -82,6 +83,7 @@ std::vector<ffloat> price_gpu(const HParams& p, const ffloat S,
   req.seed = opt.seed;
   req.normal_mode = opt.normal_mode;
   req.rng_mode = opt.rng_mode;
+  req.schedule_mode = opt.schedule_mode;
   req.n_streams = opt.n_streams;
   std::vector<ffloat> prices(n_opts);
   if (opt.stderr_out) opt.stderr_out->assign(n_opts, 0.0);

@@ -176,7 +176,7 @@ __global__ void qe_replay_kernel(double v0, double S, double lnS, uint32_t n_seg
   for (uint32_t k = 0; k < n_seg; ++k) {
     const SegConst g = segs[k];
     const uint32_t n = g.n_steps;
-    if (PAYOFF == HEXO_PAYOFF_ASIAN && k > 0 && n > 0) integral += g.h * 0.5 * (X + Xprev);
+    if (PAYOFF == HEXO_PAYOFF_ASIAN && k > 0 && n > 0) integral += g.hcarry * (X + Xprev);
     const double Xa = X;
     double sumX = 0.0;
     for (uint32_t i = 0; i < n; ++i, ++step) {
@@ -199,7 +199,8 @@ __global__ void qe_replay_kernel(double v0, double S, double lnS, uint32_t n_seg
     if (PAYOFF == HEXO_PAYOFF_ASIAN && n > 0) integral += g.h * 0.5 * (Xa - Xprev + 2.0 * sumX);
     const double dx = X - Xprev;
     finals[path * n_seg + k] =
-        PAYOFF == HEXO_PAYOFF_ASIAN ? (integral + dx * g.w) / g.expiry : Xprev + dx * g.w;
+        PAYOFF == HEXO_PAYOFF_ASIAN ? (integral + dx * g.w + g.hs * (X + Xprev)) / g.expiry
+                                    : Xprev + dx * g.w;
   }
 }
 
@@ -261,6 +262,32 @@ static int build_schedule(const double* expiries, uint32_t n_chains, uint32_t st
   return HEXO_OK;
 }
 
+// HEXO_SCHEDULE_EXACT: a time grid that ends on every expiry.  Segment k covers
+// (T_{k-1}, T_k] with n_k = max(1, round((T_k - T_{k-1}) steps / T_k)) steps of width
+// (T_k - T_{k-1}) / n_k -- `steps` keeps the reference's meaning "steps per the expiry currently
+// headed for" (AsianContract.h:35-38) -- and the last step counts fully (w = 1).
+static int build_schedule_exact(const double* expiries, uint32_t n_chains, uint32_t steps,
+                                hexo_segment* seg) {
+  if (!expiries || !seg || n_chains == 0 || steps == 0)
+    return fail(HEXO_ERR_INVALID_ARGUMENT, "schedule: need expiries, n_chains>0, steps>0");
+  if (!(expiries[0] > 0.0) || !std::isfinite(expiries[0]))
+    return fail(HEXO_ERR_NOT_INCREASING, "first expiry must be positive and finite");
+  double prev = 0.0;
+  for (uint32_t k = 0; k < n_chains; ++k) {
+    if (k > 0 && (!(expiries[k - 1] < expiries[k]) || !std::isfinite(expiries[k])))
+      return fail(HEXO_ERR_NOT_INCREASING, "expiries must be strictly increasing (chain %u)", k);
+    const double span = expiries[k] - prev;
+    long long n = llround(span * (double)steps / expiries[k]);
+    if (n < 1) n = 1;
+    seg[k].n_steps = (uint32_t)n;
+    seg[k].h = span / (double)n;
+    seg[k].w = 1.0;
+    seg[k].expiry = expiries[k];
+    prev = expiries[k];
+  }
+  return HEXO_OK;
+}
+
 static int check_request(const hexo_price_request* r, bool need_strikes) {
   if (!r) return fail(HEXO_ERR_INVALID_ARGUMENT, "request is NULL");
   if (r->n_chains == 0 || !r->expiries) return fail(HEXO_ERR_INVALID_ARGUMENT, "no chains");
@@ -271,6 +298,8 @@ static int check_request(const hexo_price_request* r, bool need_strikes) {
     return fail(HEXO_ERR_INVALID_ARGUMENT, "unknown normal_mode %d", r->normal_mode);
   if (r->rng_mode != HEXO_RNG_SHISHUA && r->rng_mode != HEXO_RNG_PHILOX)
     return fail(HEXO_ERR_INVALID_ARGUMENT, "unknown rng_mode %d", r->rng_mode);
+  if (r->schedule_mode != HEXO_SCHEDULE_REFERENCE && r->schedule_mode != HEXO_SCHEDULE_EXACT)
+    return fail(HEXO_ERR_INVALID_ARGUMENT, "unknown schedule_mode %d", r->schedule_mode);
   // The reference divides by kappa and sigma (HSimulation.tpp:60,75-77) and takes log(S) (:90);
   // it would silently produce NaN prices.  Refuse instead.
   const hexo_hparams& p = r->p;
@@ -301,7 +330,9 @@ static int check_request(const hexo_price_request* r, bool need_strikes) {
 static int build_segments(const hexo_price_request* r, bool with_strikes,
                           std::vector<SegConst>& out, uint64_t* steps_per_path) {
   std::vector<hexo_segment> sched(r->n_chains);
-  int rc = build_schedule(r->expiries, r->n_chains, r->steps, sched.data());
+  const bool exact = r->schedule_mode == HEXO_SCHEDULE_EXACT;
+  int rc = exact ? build_schedule_exact(r->expiries, r->n_chains, r->steps, sched.data())
+                 : build_schedule(r->expiries, r->n_chains, r->steps, sched.data());
   if (rc) return rc;
   const double theta = r->p.v_m, rho = r->p.rho, kappa = r->p.kappa, eps = r->p.sigma;
   out.resize(r->n_chains);
@@ -311,6 +342,15 @@ static int build_segments(const hexo_price_request* r, bool with_strikes,
     const double h = sched[k].h;
     g.h = h;
     g.w = sched[k].w;
+    g.hcarry = h * 0.5;  // HSimulation.tpp:42-44: the crossing trapezoid takes the NEW step width
+    g.hs = 0.0;
+    if (exact) {
+      g.hcarry = k > 0 ? sched[k - 1].h * 0.5 : 0.0;
+      if (r->payoff == HEXO_PAYOFF_ASIAN) {  // full trapezoid of the last step instead of dx * w
+        g.w = 0.0;
+        g.hs = h * 0.5;
+      }
+    }
     g.expiry = sched[k].expiry;
     g.n_steps = sched[k].n_steps;
     total += g.n_steps;
@@ -592,6 +632,11 @@ int hexo_gpu_shutdown(void) {
 int hexo_gpu_schedule(const double* expiries, uint32_t n_chains, uint32_t steps,
                       hexo_segment* segments_out) {
   return build_schedule(expiries, n_chains, steps, segments_out);
+}
+
+int hexo_gpu_schedule_exact(const double* expiries, uint32_t n_chains, uint32_t steps,
+                            hexo_segment* segments_out) {
+  return build_schedule_exact(expiries, n_chains, steps, segments_out);
 }
 
 uint64_t hexo_gpu_default_streams(uint64_t n_paths, uint32_t n_opts, int n_gpus) {

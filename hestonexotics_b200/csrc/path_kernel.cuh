@@ -314,7 +314,7 @@ heston_qe_paths_kernel(const __grid_constant__ PathArgs a) {
           // The trapezoid of the step that crossed the previous expiry is added
           // AFTER update_earliest switched the step size (HSimulation.tpp:42-44),
           // i.e. with this segment's h.
-          integral += g.h * 0.5 * (X + Xprev);
+          integral += g.hcarry * (X + Xprev);
         }
         const double Xa = X;
         double sumX = 0.0;
@@ -394,7 +394,8 @@ heston_qe_paths_kernel(const __grid_constant__ PathArgs a) {
       }
       // accumulate_final_value, AsianContract.h:29-34 / VanillaContract.h:28-31
       const double dx = X - Xprev;
-      const double fv = kAsian ? (integral + dx * g.w) / g.expiry : Xprev + dx * g.w;
+      const double fv =
+          kAsian ? (integral + dx * g.w + g.hs * (X + Xprev)) / g.expiry : Xprev + dx * g.w;
       __syncwarp();
       fvbuf[lane] = fv;
       const unsigned amask = __ballot_sync(0xffffffffu, active);

@@ -118,7 +118,7 @@ heston_qe_paths_il_kernel(const __grid_constant__ PathArgs a) {
       g.K0 = pin(g.K0); g.K1 = pin(g.K1); g.K2 = pin(g.K2); g.K3 = pin(g.K3);
       if (active) {
         const uint32_t n = g.n_steps;
-        if (kAsian && k > 0 && n > 0) integral += g.h * 0.5 * (X + Xprev);  // HSimulation.tpp:42-44
+        if (kAsian && k > 0 && n > 0) integral += g.hcarry * (X + Xprev);  // HSimulation.tpp:42-44
         const double Xa = X;
         double sumX = 0.0;
         auto spot_half = [&](double Vfrom, double Vto, double zx, auto with_x) {
@@ -163,7 +163,8 @@ heston_qe_paths_il_kernel(const __grid_constant__ PathArgs a) {
       }
       // accumulate_final_value, AsianContract.h:29-34 / VanillaContract.h:28-31
       const double dx = X - Xprev;
-      const double fv = kAsian ? (integral + dx * g.w) / g.expiry : Xprev + dx * g.w;
+      const double fv =
+          kAsian ? (integral + dx * g.w + g.hs * (X + Xprev)) / g.expiry : Xprev + dx * g.w;
       __syncwarp();
       fvbuf[lane] = fv;
       const unsigned amask = __ballot_sync(0xffffffffu, active);

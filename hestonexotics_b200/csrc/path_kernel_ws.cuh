@@ -261,7 +261,7 @@ heston_qe_paths_ws_kernel(const __grid_constant__ PathArgs a, const uint32_t ste
         g.D = pin(g.D); g.m0 = pin(g.m0); g.c1h = pin(g.c1h); g.c2h = pin(g.c2h);
         g.K0 = pin(g.K0); g.K1 = pin(g.K1); g.K2 = pin(g.K2); g.K3 = pin(g.K3);
         const uint32_t n = g.n_steps;
-        if (kAsian && k > 0 && n > 0) integral += g.h * 0.5 * (X + Xprev);
+        if (kAsian && k > 0 && n > 0) integral += g.hcarry * (X + Xprev);
         const double Xa = X;
         double sumX = 0.0;
         auto spot_half = [&](double Vfrom, double Vto, double zx, auto with_x) {
@@ -315,7 +315,8 @@ heston_qe_paths_ws_kernel(const __grid_constant__ PathArgs a, const uint32_t ste
           if (n > 0) run(min(n, 2u), std::true_type{});
         }
         const double dx = X - Xprev;
-        const double fv = kAsian ? (integral + dx * g.w) / g.expiry : Xprev + dx * g.w;
+        const double fv =
+            kAsian ? (integral + dx * g.w + g.hs * (X + Xprev)) / g.expiry : Xprev + dx * g.w;
         __syncwarp();
         fvbuf[lane] = fv;
         const unsigned amask = __ballot_sync(0xffffffffu, active);

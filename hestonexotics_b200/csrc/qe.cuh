@@ -28,9 +28,13 @@ namespace hexo {
 
 // One maturity ("segment") of a price<>() call.  While heading for expiry k the
 // reference steps with h = expiry_k/steps (AsianContract.h:35-38); n_steps and w
-// come from the host schedule (hexo_gpu_schedule).
+// come from the host schedule (hexo_gpu_schedule / hexo_gpu_schedule_exact).
 struct SegConst {
   double h, w, expiry;
+  // Asian trapezoid bookkeeping.  Reference schedule: hcarry = h/2 (the trapezoid of the step
+  // that crossed the previous expiry is added with THIS segment's h, HSimulation.tpp:42-44) and
+  // hs = 0.  Exact schedule (HEXO_SCHEDULE_EXACT): hcarry = h_{k-1}/2, w = 0, hs = h/2.
+  double hcarry, hs;
   double D;         // exp(-kappa h)                                      (:58)
   double m0;        // theta (1 - D):  m = V D + m0                        (:59)
   double c1h, c2h;  // s^2/2 = |V c1h + c2h|                               (:60)

@@ -41,6 +41,7 @@ class HQEAnderson:
 _NORMAL_MODES = {"f32": _lib.NORMAL_F32, "as-built": _lib.NORMAL_F32, "f64": _lib.NORMAL_F64,
                  _lib.NORMAL_F32: _lib.NORMAL_F32, _lib.NORMAL_F64: _lib.NORMAL_F64}
 _RNG_MODES = {"shishua": 0, "philox": 1, 0: 0, 1: 1}   # hexo_rng_mode
+_GRID_MODES = {"reference": 0, "exact": 1, 0: 0, 1: 1}  # hexo_schedule_mode
 
 
 @dataclass
@@ -62,7 +63,7 @@ class _Request:
 
     def __init__(self, scheme, p: HParams, S: float, all_chains: Sequence[OptionsChain],
                  n_simulations: int, n_opts: Optional[int], steps: int, seed: int, normal_mode,
-                 n_streams: int, rng="shishua"):
+                 n_streams: int, rng="shishua", time_grid="reference"):
         if isinstance(scheme, type) and hasattr(scheme, "payoff"):
             scheme = HQEAnderson(scheme)
         self.expiries, self.offsets, self.strikes = flatten_chains(all_chains)
@@ -74,13 +75,15 @@ class _Request:
             raise ValueError(f"normal_mode must be 'f32' or 'f64', got {normal_mode!r}")
         if rng not in _RNG_MODES:
             raise ValueError(f"rng must be 'shishua' or 'philox', got {rng!r}")
+        if time_grid not in _GRID_MODES:
+            raise ValueError(f"time_grid must be 'reference' or 'exact', got {time_grid!r}")
         self.req = _lib.HexoPriceRequest(
             _lib.HexoHParams(*p.as_tuple()), float(S), scheme.payoff, len(self.expiries),
             self.expiries.ctypes.data_as(_lib.c_double_p),
             self.offsets.ctypes.data_as(_lib.c_uint32_p),
             self.strikes.ctypes.data_as(_lib.c_double_p),
             int(n_simulations), int(steps), int(seed), _NORMAL_MODES[normal_mode],
-            _RNG_MODES[rng], int(n_streams))
+            _RNG_MODES[rng], int(n_streams), _GRID_MODES[time_grid], 0)
 
 
 def _finish(sums: np.ndarray, n_paths: int, n_opts: int):
@@ -96,13 +99,13 @@ def _finish(sums: np.ndarray, n_paths: int, n_opts: int):
 def price_full(scheme, p: HParams, S: float, all_chains: Sequence[OptionsChain],
                n_simulations: int, n_opts: Optional[int], steps: int, *, seed: int = 1,
                normal_mode="f32", n_streams: int = 0, rng="shishua",
-               device: Optional[int] = None) -> PriceResult:
+               time_grid="reference", device: Optional[int] = None) -> PriceResult:
     """price<Scheme>() on one GPU, returning prices, standard errors and launch statistics."""
     lib = _lib.load()
     if device is not None:
         _lib.check(lib.hexo_gpu_init(int(device)))
     rq = _Request(scheme, p, S, all_chains, n_simulations, n_opts, steps, seed, normal_mode,
-                  n_streams, rng)
+                  n_streams, rng, time_grid)
     if rq.req.n_streams == 0:
         rq.req.n_streams = lib.hexo_gpu_default_streams(rq.req.n_paths, rq.n_opts, 1)
     sums = np.zeros(2 * rq.n_opts, dtype=np.float64)
@@ -117,12 +120,13 @@ def price_full(scheme, p: HParams, S: float, all_chains: Sequence[OptionsChain],
 
 def price_multi(scheme, p: HParams, S: float, all_chains: Sequence[OptionsChain],
                 n_simulations: int, n_opts: Optional[int], steps: int, *, n_gpus: int = 0,
-                seed: int = 1, normal_mode="f32", n_streams: int = 0, rng="shishua"):
+                seed: int = 1, normal_mode="f32", n_streams: int = 0, rng="shishua",
+                time_grid="reference"):
     """price<Scheme>() spread over several GPUs of THIS process (hexo_gpu_price_multi); returns
     (prices, stderr).  n_gpus = 0 uses every visible device."""
     lib = _lib.load()
     rq = _Request(scheme, p, S, all_chains, n_simulations, n_opts, steps, seed, normal_mode,
-                  n_streams, rng)
+                  n_streams, rng, time_grid)
     prices, se = np.zeros(rq.n_opts), np.zeros(rq.n_opts)
     _lib.check(lib.hexo_gpu_price_multi(C.byref(rq.req), int(n_gpus),
                                         prices.ctypes.data_as(_lib.c_double_p),
@@ -132,7 +136,8 @@ def price_multi(scheme, p: HParams, S: float, all_chains: Sequence[OptionsChain]
 
 def price_batch(scheme, params: Sequence[HParams], S: float, all_chains: Sequence[OptionsChain],
                 n_simulations: int, n_opts: Optional[int], steps: int, *, seeds=1,
-                normal_mode="f32", n_streams: int = 0, rng="shishua", n_lanes: int = 0):
+                normal_mode="f32", n_streams: int = 0, rng="shishua", time_grid="reference",
+                n_lanes: int = 0):
     """price<Scheme>() of the same chains for MANY parameter sets in one submission
     (hexo_gpu_price_batch): the shape of Monte-Carlo pricing inside a calibration loop.  `seeds`
     is one seed for all jobs (common random numbers) or one per parameter set.  Returns
@@ -145,7 +150,7 @@ def price_batch(scheme, params: Sequence[HParams], S: float, all_chains: Sequenc
     if len(seeds) != len(params):
         raise ValueError("one seed per parameter set")
     rqs = [_Request(scheme, p, S, all_chains, n_simulations, n_opts, steps, sd, normal_mode,
-                    n_streams, rng) for p, sd in zip(params, seeds)]
+                    n_streams, rng, time_grid) for p, sd in zip(params, seeds)]
     arr = (_lib.HexoPriceRequest * len(rqs))(*[r.req for r in rqs])
     n = rqs[0].n_opts
     prices, se = np.zeros((len(rqs), n)), np.zeros((len(rqs), n))
@@ -171,7 +176,8 @@ def shard_range(n_streams: int, rank: int, world_size: int):
 
 def price_distributed(scheme, p: HParams, S: float, all_chains: Sequence[OptionsChain],
                       n_simulations: int, n_opts: Optional[int], steps: int, *, seed: int = 1,
-                      normal_mode="f32", n_streams: int = 0, rng="shishua", group=None,
+                      normal_mode="f32", n_streams: int = 0, rng="shishua",
+                      time_grid="reference", group=None,
                       _shard_sums=None) -> PriceResult:
     """price<Scheme>() sharded over the ranks of a torch.distributed group.
 
@@ -186,7 +192,7 @@ def price_distributed(scheme, p: HParams, S: float, all_chains: Sequence[Options
 
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     rq = _Request(scheme, p, S, all_chains, n_simulations, n_opts, steps, seed, normal_mode,
-                  n_streams, rng)
+                  n_streams, rng, time_grid)
     stats = _lib.HexoGpuStats()
     if _shard_sums is None:
         lib = _lib.load()
@@ -214,10 +220,11 @@ def price_distributed(scheme, p: HParams, S: float, all_chains: Sequence[Options
                        int(stats.grid), int(stats.block))
 
 
-def schedule(expiries: Sequence[float], steps: int):
+def schedule(expiries: Sequence[float], steps: int, time_grid="reference"):
     """Step schedule of a price<>() call (host only): list of (n_steps, h, w, expiry)."""
     lib = _lib.load()
     ex = np.ascontiguousarray(expiries, dtype=np.float64)
     seg = (_lib.HexoSegment * len(ex))()
-    _lib.check(lib.hexo_gpu_schedule(ex.ctypes.data_as(_lib.c_double_p), len(ex), int(steps), seg))
+    fn = lib.hexo_gpu_schedule_exact if _GRID_MODES[time_grid] else lib.hexo_gpu_schedule
+    _lib.check(fn(ex.ctypes.data_as(_lib.c_double_p), len(ex), int(steps), seg))
     return [(s.n_steps, s.h, s.w, s.expiry) for s in seg]

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define HEXO_GPU_ABI_VERSION 2 /* 2: rng_mode in hexo_price_request (former padding) */
+#define HEXO_GPU_ABI_VERSION 2 /* 2: rng_mode, schedule_mode in hexo_price_request */
 
 typedef enum {
   HEXO_OK = 0,
@@ -56,6 +56,15 @@ typedef enum { HEXO_NORMAL_F32 = 0, HEXO_NORMAL_F64 = 1 } hexo_normal_mode;
  * the n-th stepper call of stream s draws Philox4x32-10(counter {n_lo,n_hi,s_lo,s_hi}, key
  * {seed_lo,seed_hi}) = (c0..c3); variance word c0|c1<<32, spot word c2|c3<<32. */
 typedef enum { HEXO_RNG_SHISHUA = 0, HEXO_RNG_PHILOX = 1 } hexo_rng_mode;
+
+/* Time grid.  REFERENCE reproduces the reference's loop bit for bit in its quirks (SURVEY
+ * finding 6, Appendix B-3..5): time advances by repeated double addition, so (T=1, steps=252)
+ * takes 253 stepper calls while (T=1, steps=1024) takes 1024 with the last trapezoid of the Asian
+ * average replaced by X_N - X_{N-1}, and after an expiry the step width switches to T_next/steps
+ * from wherever the grid stands.  EXACT is the corrected grid: segment k covers (T_{k-1}, T_k]
+ * with n_k = max(1, round((T_k - T_{k-1}) steps / T_k)) steps of equal width, the Asian average
+ * is the full trapezoid rule and the European payoff reads X at the last step. */
+typedef enum { HEXO_SCHEDULE_REFERENCE = 0, HEXO_SCHEDULE_EXACT = 1 } hexo_schedule_mode;
 
 /* HParams, src/inc/HDistribution.h:9-24 -- same field order, same meaning */
 typedef struct {
@@ -89,6 +98,8 @@ typedef struct {
                                   /* For a fixed (seed,n_paths,n_streams) the   */
                                   /* sums do not depend on how streams are      */
                                   /* sharded over GPUs.                         */
+  int32_t schedule_mode;          /* hexo_schedule_mode; 0 = the reference's    */
+  int32_t reserved;               /* must be 0                                  */
 } hexo_price_request;
 
 typedef struct {
@@ -123,6 +134,9 @@ const char *hexo_gpu_last_error(void);
 /* ---- host-side schedule (no GPU needed) ------------------------------------ */
 int hexo_gpu_schedule(const double *expiries, uint32_t n_chains, uint32_t steps,
                       hexo_segment *segments_out /* [n_chains] */);
+/* the same for HEXO_SCHEDULE_EXACT (w is 1 for every segment) */
+int hexo_gpu_schedule_exact(const double *expiries, uint32_t n_chains, uint32_t steps,
+                            hexo_segment *segments_out);
 
 /* ---- K1: the fused pricing path --------------------------------------------
  * Replaces HSimulation::price<Scheme> (HSimulation.tpp:10-51).  prices_out

@@ -523,6 +523,64 @@ int oracle_price_stream_rng(const oracle_contract *c, int rng_mode, uint64_t see
   return 0;
 }
 
+/* ---- corrected time grid (NOT the reference's loop; include/hexo_gpu.h, HEXO_SCHEDULE_EXACT) --
+ * Segment k covers (T_{k-1}, T_k] with n_k = max(1, round((T_k - T_{k-1}) steps / T_k)) steps
+ * of equal width; the Asian average is the full trapezoid rule over [0, T_k], the European
+ * payoff reads X at the last step.  The stepper itself is the reference's (qe_step). */
+static uint32_t simulate_path_exact(const oracle_contract *c, draw_src *d, pay_fn pay,
+                                    void *pay_ctx) {
+  policy o;
+  memset(&o, 0, sizeof(o));
+  o.payoff = c->payoff;
+  sde_state st = {c->S, c->p.v_0, c->S, c->p.v_0, 0.0, 0.0, log(c->S)};
+  double integral = 0.0, t_prev = 0.0;
+  uint32_t total = 0;
+  for (uint32_t k = 0; k < c->n_chains; ++k) {
+    const double span = c->expiries[k] - t_prev;
+    long long n = llround(span * (double)c->steps / c->expiries[k]);
+    if (n < 1) n = 1;
+    o.init_step_size = span / (double)n; /* qe_step reads its step width here */
+    o.earliest_unpriced_expi = c->expiries[k];
+    for (long long j = 0; j < n; ++j) {
+      qe_step(&c->p, &st, &o, d);
+      integral += o.init_step_size * .5 * (st.cur_X + st.prev_X);
+      ++total;
+    }
+    o.final_value = c->payoff == ORACLE_ASIAN ? integral / c->expiries[k] : st.cur_X;
+    pay(pay_ctx, k, &o);
+    t_prev = c->expiries[k];
+  }
+  return total;
+}
+
+int oracle_price_stream_exact(const oracle_contract *c, int rng_mode, uint64_t seed,
+                              uint64_t n_paths, uint64_t n_streams_total, uint64_t stream_begin,
+                              uint64_t stream_count, int normal_mode, double *sum, double *sumsq) {
+  int rc = check_contract(c);
+  if (rc) return rc;
+  if (n_streams_total == 0 || stream_begin + stream_count > n_streams_total) return -1;
+  const uint32_t n_opts = c->strike_offsets[c->n_chains];
+  if (sum) memset(sum, 0, n_opts * sizeof(double));
+  if (sumsq) memset(sumsq, 0, n_opts * sizeof(double));
+  sum_sink sink = {c, NULL, sum, sumsq, (double)n_paths};
+  const uint64_t base = n_paths / n_streams_total, rem = n_paths % n_streams_total;
+  for (uint64_t s = stream_begin; s < stream_begin + stream_count; ++s) {
+    stream_ctx sc;
+    memset(&sc, 0, sizeof(sc));
+    uint64_t sd[4] = {seed, s, 0, 0};
+    prng_init(&sc.s, sd);
+    sc.pos = 16;
+    sc.normal_mode = normal_mode;
+    sc.rng_mode = rng_mode;
+    sc.seed = seed;
+    sc.stream = s;
+    draw_src d = {strsrc_gv, strsrc_uv, strsrc_gx, strsrc_end, &sc};
+    const uint64_t my_paths = base + (s < rem ? 1 : 0);
+    for (uint64_t i = 0; i < my_paths; ++i) simulate_path_exact(c, &d, pay_sums, &sink);
+  }
+  return 0;
+}
+
 int oracle_replay(const oracle_contract *c, const double *tape, uint64_t n_paths,
                   uint32_t tape_steps, double *finals) {
   int rc = check_contract(c);

@@ -99,6 +99,14 @@ int oracle_price_stream_rng(const oracle_contract *c, int rng_mode, uint64_t see
                             uint64_t n_streams_total, uint64_t stream_begin, uint64_t stream_count,
                             int normal_mode, double *sum, double *sumsq);
 
+/* The corrected time grid of include/hexo_gpu.h (HEXO_SCHEDULE_EXACT) -- NOT the reference's
+ * loop: segment k covers (T_{k-1}, T_k] with n_k = max(1, round((T_k - T_{k-1}) steps / T_k))
+ * equal steps, full trapezoid rule for the Asian average, X at the last step for the European
+ * payoff.  Same stepper, same stream convention as oracle_price_stream_rng. */
+int oracle_price_stream_exact(const oracle_contract *c, int rng_mode, uint64_t seed,
+                              uint64_t n_paths, uint64_t n_streams_total, uint64_t stream_begin,
+                              uint64_t stream_count, int normal_mode, double *sum, double *sumsq);
+
 /* ---- tape replay ------------------------------------------------------------
  * tape[path][step][3] = {Z_V, U_V, Z_X}; the stepper takes Z_V or U_V according
  * to its branch.  finals[path][chain] receives the policy's final_value (Asian

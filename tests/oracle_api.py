@@ -73,6 +73,7 @@ def oracle() -> C.CDLL:
         o.oracle_price_stream_rng.argtypes = [C.POINTER(OracleContract), C.c_int, C.c_uint64,
                                               C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64,
                                               C.c_int, dp, dp]
+        o.oracle_price_stream_exact.argtypes = o.oracle_price_stream_rng.argtypes
         o.oracle_philox4x32_10.argtypes = [C.POINTER(C.c_uint32)] * 3
         o.oracle_philox4x32_10.restype = None
         o.oracle_replay.argtypes = [C.POINTER(OracleContract), dp, C.c_uint64, C.c_uint32, dp]
@@ -133,12 +134,12 @@ class Contract:
         return pr, sm, sq
 
     def price_stream(self, seed, n_paths, n_streams, begin=0, count=None,
-                     normal_mode=NORMAL_F32, rng_mode=0):
+                     normal_mode=NORMAL_F32, rng_mode=0, exact_grid=False):
         count = n_streams - begin if count is None else count
         sm, sq = np.zeros(self.n_opts), np.zeros(self.n_opts)
-        rc = oracle().oracle_price_stream_rng(C.byref(self.c), rng_mode, seed, n_paths, n_streams,
-                                              begin, count, normal_mode, sm.ctypes.data_as(dp),
-                                              sq.ctypes.data_as(dp))
+        fn = oracle().oracle_price_stream_exact if exact_grid else oracle().oracle_price_stream_rng
+        rc = fn(C.byref(self.c), rng_mode, seed, n_paths, n_streams, begin, count, normal_mode,
+                sm.ctypes.data_as(dp), sq.ctypes.data_as(dp))
         assert rc == 0, rc
         return sm, sq
 

@@ -40,7 +40,7 @@ def test_struct_layout_matches_header(hexo_lib):
     assert [f[0] for f in _lib.HexoHParams._fields_] == ["v_0", "v_m", "rho", "kappa", "sigma"]
     assert C.sizeof(_lib.HexoHParams) == 40
     assert C.sizeof(_lib.HexoSegment) == 32
-    assert C.sizeof(_lib.HexoPriceRequest) == 40 + 8 + 8 + 24 + 8 + 8 + 8 + 8 + 8
+    assert C.sizeof(_lib.HexoPriceRequest) == 40 + 8 + 8 + 24 + 8 + 8 + 8 + 8 + 8 + 8
 
 
 @pytest.mark.parametrize("expiries,steps", [
