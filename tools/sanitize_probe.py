@@ -1,0 +1,24 @@
+"""Small pricing calls for compute-sanitizer (memcheck / racecheck / initcheck / synccheck):
+every kernel variant of the default path on tiny problems."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import hestonexotics_b200 as hx
+
+p = hx.HParams(0.04, 0.04, -0.7, 2.0, 0.5)
+A = hx.HQEAnderson(hx.AAsianCallNonAdaptive)
+E = hx.HQEAnderson(hx.EuropeanCallNonAdaptive)
+one = [hx.OptionsChain.from_strikes(1.0, [100.0])]
+many = [hx.OptionsChain.from_strikes(0.1 * (k + 1), list(np.linspace(80, 120, 5))) for k in range(12)]
+wide = [hx.OptionsChain.from_strikes(1.0, list(np.linspace(50, 150, 3000)))]
+for scheme in (A, E):
+    for nm in ("f32", "f64"):
+        for rng in ("shishua", "philox"):
+            for grid in ("reference", "exact"):
+                r = hx.price_full(scheme, p, 100.0, one, 700, None, 20, normal_mode=nm, rng=rng,
+                                  time_grid=grid, n_streams=300)
+                assert np.isfinite(r.prices).all()
+    r = hx.price_full(scheme, p, 100.0, many, 500, None, 6, n_streams=257)   # > 8 segments
+    r = hx.price_full(scheme, p, 100.0, wide, 300, None, 4, n_streams=64)    # device accumulators
+pr, se, ms = hx.price_batch(A, [p, p, p], 100.0, one, 500, None, 10, n_lanes=2)
+print("sanitize probe ok", r.prices[:2], pr[:, 0])
