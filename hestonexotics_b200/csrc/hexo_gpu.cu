@@ -387,31 +387,26 @@ struct Plan {
 };
 
 typedef void (*PathKernel)(const PathArgs);
-template <bool INL>
+template <int SEGS, class Gen>
 static PathKernel pick_kernel_t(int payoff, int normal_mode) {
   if (payoff == HEXO_PAYOFF_ASIAN)
-    return normal_mode == HEXO_NORMAL_F64 ? heston_qe_paths_kernel<HEXO_PAYOFF_ASIAN, 1, INL>
-                                          : heston_qe_paths_kernel<HEXO_PAYOFF_ASIAN, 0, INL>;
-  return normal_mode == HEXO_NORMAL_F64 ? heston_qe_paths_kernel<HEXO_PAYOFF_EUROPEAN, 1, INL>
-                                        : heston_qe_paths_kernel<HEXO_PAYOFF_EUROPEAN, 0, INL>;
+    return normal_mode == HEXO_NORMAL_F64
+               ? heston_qe_paths_kernel<HEXO_PAYOFF_ASIAN, 1, SEGS, Gen>
+               : heston_qe_paths_kernel<HEXO_PAYOFF_ASIAN, 0, SEGS, Gen>;
+  return normal_mode == HEXO_NORMAL_F64
+             ? heston_qe_paths_kernel<HEXO_PAYOFF_EUROPEAN, 1, SEGS, Gen>
+             : heston_qe_paths_kernel<HEXO_PAYOFF_EUROPEAN, 0, SEGS, Gen>;
+}
+template <class Gen>
+static PathKernel pick_kernel_g(int payoff, int normal_mode, uint32_t n_seg) {
+  return n_seg == 1                       ? pick_kernel_t<kSegsSingle, Gen>(payoff, normal_mode)
+         : n_seg <= (uint32_t)kInlineSegs ? pick_kernel_t<kSegsInline, Gen>(payoff, normal_mode)
+                                          : pick_kernel_t<kSegsGlobal, Gen>(payoff, normal_mode);
 }
 // Philox mode: only the default kernel shape carries it (not the WS / IL experiments)
-template <bool INL>
-static PathKernel pick_philox_kernel_t(int payoff, int normal_mode) {
-  if (payoff == HEXO_PAYOFF_ASIAN)
-    return normal_mode == HEXO_NORMAL_F64
-               ? heston_qe_paths_kernel<HEXO_PAYOFF_ASIAN, 1, INL, PhiloxGen>
-               : heston_qe_paths_kernel<HEXO_PAYOFF_ASIAN, 0, INL, PhiloxGen>;
-  return normal_mode == HEXO_NORMAL_F64
-             ? heston_qe_paths_kernel<HEXO_PAYOFF_EUROPEAN, 1, INL, PhiloxGen>
-             : heston_qe_paths_kernel<HEXO_PAYOFF_EUROPEAN, 0, INL, PhiloxGen>;
-}
 static PathKernel pick_kernel(int payoff, int normal_mode, uint32_t n_seg, int rng_mode = 0) {
-  if (rng_mode == HEXO_RNG_PHILOX)
-    return n_seg <= (uint32_t)kInlineSegs ? pick_philox_kernel_t<true>(payoff, normal_mode)
-                                          : pick_philox_kernel_t<false>(payoff, normal_mode);
-  return n_seg <= (uint32_t)kInlineSegs ? pick_kernel_t<true>(payoff, normal_mode)
-                                        : pick_kernel_t<false>(payoff, normal_mode);
+  return rng_mode == HEXO_RNG_PHILOX ? pick_kernel_g<PhiloxGen>(payoff, normal_mode, n_seg)
+                                     : pick_kernel_g<Shishua>(payoff, normal_mode, n_seg);
 }
 
 typedef void (*PathKernelWs)(const PathArgs, const uint32_t);

@@ -242,7 +242,14 @@ struct ZRing<HEXO_NORMAL_F64> {
   }
 };
 
-template <int PAYOFF, int NORMAL_MODE, bool INLINE_SEGS, class Gen = Shishua>
+// Where the per-maturity constants are read from: global memory (any number of maturities), the
+// kernel parameter bank indexed by the maturity (up to kInlineSegs), or -- one maturity, the
+// benchmark shape -- fixed parameter-bank addresses, which the compiler can keep in uniform
+// registers: a DFMA takes one uniform-register operand for free, so every DFMA of the step loop
+// then reads at most two register pairs.
+enum : int { kSegsGlobal = 0, kSegsInline = 1, kSegsSingle = 2 };
+
+template <int PAYOFF, int NORMAL_MODE, int SEGS, class Gen = Shishua>
 __global__ void __launch_bounds__(kMaxBlock, kMinBlocksPerSM)
 heston_qe_paths_kernel(const __grid_constant__ PathArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -276,8 +283,16 @@ heston_qe_paths_kernel(const __grid_constant__ PathArgs a) {
   const uint64_t sid = a.stream_begin + slot;
   const uint64_t my_paths =
       slot < a.stream_count ? a.base_paths + (sid < a.rem_streams ? 1u : 0u) : 0u;
-  // path counts are non-increasing in the stream id, so lane 0 holds the warp's maximum
-  const uint64_t warp_paths = __shfl_sync(0xffffffffu, my_paths, 0);
+  // Path counts are non-increasing in the stream id, so the block's first stream holds the
+  // block's maximum.  It depends on blockIdx and kernel parameters only: every loop below is
+  // uniform across the block as far as the compiler can prove, which lets it keep loop counters,
+  // strides and constants in uniform registers.  Lanes whose own stream has fewer paths run
+  // along and are masked out where payoffs are accumulated.
+  const uint64_t block_first = (uint64_t)blockIdx.x * T;
+  const uint64_t block_paths =
+      block_first < a.stream_count
+          ? a.base_paths + (a.stream_begin + block_first < a.rem_streams ? 1u : 0u)
+          : 0u;
 
   Gen rng;  // Shishua (the reference's generator) or PhiloxGen (optional counter mode)
   auto refill = [&](uint64_t (&o)[16]) {
@@ -296,19 +311,22 @@ heston_qe_paths_kernel(const __grid_constant__ PathArgs a) {
   uint32_t pos = 0;  // next unread step of the round
   __syncthreads();   // exptab
 
-  for (uint64_t p = 0; p < warp_paths; ++p) {
+  for (uint64_t p = 0; p < block_paths; ++p) {
     const bool active = p < my_paths;
     // HQEAnderson::operator=(initial_state), HSimulation.tpp:26,87-94
     double V = a.v0, lnX = a.lnS, X = a.S, Xprev = a.S;
     double integral = 0.0;  // AAsianCallNonAdaptive::accumulated_value, reset per path (:34)
-    for (uint32_t k = 0; k < a.n_seg; ++k) {
-      // INLINE_SEGS: read the constants straight from the parameter bank (k is uniform)
-      SegConst g = INLINE_SEGS ? a.seg_inline[k] : a.segs[k];
+    for (uint32_t k = 0; k < (SEGS == kSegsSingle ? 1u : a.n_seg); ++k) {
+      SegConst g = SEGS == kSegsSingle   ? a.seg_inline[0]
+                   : SEGS == kSegsInline ? a.seg_inline[k]
+                                         : a.segs[k];
       // keep the per-step constants in registers: otherwise ptxas re-loads each of them from
       // the constant bank (LDC) at every use inside the step loop
-      g.D = pin(g.D); g.m0 = pin(g.m0); g.c1h = pin(g.c1h); g.c2h = pin(g.c2h);
-      g.K0 = pin(g.K0); g.K1 = pin(g.K1); g.K2 = pin(g.K2); g.K3 = pin(g.K3);
-      if (active) {
+      if (SEGS != kSegsSingle) {
+        g.D = pin(g.D); g.m0 = pin(g.m0); g.c1h = pin(g.c1h); g.c2h = pin(g.c2h);
+        g.K0 = pin(g.K0); g.K1 = pin(g.K1); g.K2 = pin(g.K2); g.K3 = pin(g.K3);
+      }
+      {
         const uint32_t n = g.n_steps;
         if (kAsian && k > 0 && n > 0) {
           // The trapezoid of the step that crossed the previous expiry is added
