@@ -295,7 +295,7 @@ def run_ours(args):
                 # `ncu --set full` capture (profiles/r01_path_kernel_ncu_raw_final.csv, a
                 # 4.1e9-path-step launch): 60 928 B read, 0 B written -- code and constants only,
                 # it does not grow with the number of paths
-                "traffic": 60928,
+                "traffic": 73728,
                 "note": "achieved = 100 algorithmic FP64 flop per path-step (SURVEY 8d) x path-steps "
                         "of one GPU / mean path-kernel time (CUDA events); peak = DFMA peak measured "
                         "in this run (hexo_gpu_measure_fp64_peak; MEASURED_PEAKS.json has no FP64 "
