@@ -21,7 +21,7 @@ ABI_SYMBOLS = (
     "hexo_gpu_measure_fp64_peak", "hexo_gpu_plan_create", "hexo_gpu_plan_launch",
     "hexo_gpu_plan_sums_device", "hexo_gpu_plan_stats", "hexo_gpu_plan_destroy",
     "hexo_gpu_philox4x32", "hexo_gpu_philox_streams", "hexo_gpu_price_batch",
-    "hexo_gpu_schedule_exact",
+    "hexo_gpu_schedule_exact", "hexo_gpu_sums_len", "hexo_gpu_finish",
 )
 # host-only semi-analytic benchmark functions of the same library (no hexo_gpu_ prefix)
 HOST_SYMBOLS = ("hexo_heston_chf", "hexo_swift_default_params", "hexo_swift_price_chain")
@@ -48,7 +48,7 @@ class HexoPriceRequest(C.Structure):
         ("expiries", c_double_p), ("strike_offsets", c_uint32_p), ("strikes", c_double_p),
         ("n_paths", C.c_uint64), ("steps", C.c_uint32), ("seed", C.c_uint64),
         ("normal_mode", C.c_int32), ("rng_mode", C.c_int32), ("n_streams", C.c_uint64),
-        ("schedule_mode", C.c_int32), ("reserved", C.c_int32),
+        ("schedule_mode", C.c_int32), ("control_variate", C.c_int32),
     ]
 
 
@@ -95,6 +95,9 @@ def load() -> C.CDLL:
     lib.hexo_gpu_last_error.restype = C.c_char_p
     lib.hexo_gpu_schedule.argtypes = [c_double_p, C.c_uint32, C.c_uint32, C.POINTER(HexoSegment)]
     lib.hexo_gpu_schedule_exact.argtypes = lib.hexo_gpu_schedule.argtypes
+    lib.hexo_gpu_sums_len.restype = C.c_size_t
+    lib.hexo_gpu_sums_len.argtypes = [C.POINTER(HexoPriceRequest)]
+    lib.hexo_gpu_finish.argtypes = [C.POINTER(HexoPriceRequest), c_double_p, c_double_p, c_double_p]
     lib.hexo_gpu_price.argtypes = [C.POINTER(HexoPriceRequest), c_double_p, c_double_p,
                                    C.POINTER(HexoGpuStats)]
     lib.hexo_gpu_price_multi.argtypes = [C.POINTER(HexoPriceRequest), C.c_int, c_double_p,

@@ -46,6 +46,7 @@ struct GpuPriceOptions {
   int normal_mode = HEXO_NORMAL_F32;      // the reference as built (as241.f90:20-25)
   int rng_mode = HEXO_RNG_SHISHUA;        // the reference's generator; HEXO_RNG_PHILOX optional
   int schedule_mode = HEXO_SCHEDULE_REFERENCE;  // the reference's time grid, quirks included
+  int control_variate = HEXO_CV_NONE;     // HEXO_CV_UNDERLYING: prices and errors use c = A_T - S
   uint64_t n_streams = 0;                 // 0 = sized for the device(s)
   int n_gpus = 1;                         // devices of this process to spread over; 0 = all
   std::vector<ffloat>* stderr_out = nullptr;  // optional Monte-Carlo standard errors
@@ -84,6 +85,7 @@ std::vector<ffloat> price_gpu(const HParams& p, const ffloat S,
   req.normal_mode = opt.normal_mode;
   req.rng_mode = opt.rng_mode;
   req.schedule_mode = opt.schedule_mode;
+  req.control_variate = opt.control_variate;
   req.n_streams = opt.n_streams;
   std::vector<ffloat> prices(n_opts);
   if (opt.stderr_out) opt.stderr_out->assign(n_opts, 0.0);

@@ -300,6 +300,8 @@ static int check_request(const hexo_price_request* r, bool need_strikes) {
     return fail(HEXO_ERR_INVALID_ARGUMENT, "unknown rng_mode %d", r->rng_mode);
   if (r->schedule_mode != HEXO_SCHEDULE_REFERENCE && r->schedule_mode != HEXO_SCHEDULE_EXACT)
     return fail(HEXO_ERR_INVALID_ARGUMENT, "unknown schedule_mode %d", r->schedule_mode);
+  if (r->control_variate != HEXO_CV_NONE && r->control_variate != HEXO_CV_UNDERLYING)
+    return fail(HEXO_ERR_INVALID_ARGUMENT, "unknown control_variate %d", r->control_variate);
   // The reference divides by kappa and sigma (HSimulation.tpp:60,75-77) and takes log(S) (:90);
   // it would silently produce NaN prices.  Refuse instead.
   const hexo_hparams& p = r->p;
@@ -371,13 +373,55 @@ static int build_segments(const hexo_price_request* r, bool with_strikes,
   return HEXO_OK;
 }
 
+// sums per request: [sum pf | sum pf^2] per option, plus with the control variate
+// [sum pf c] per option and [sum c | sum c^2] per maturity
+static size_t sums_len(const hexo_price_request* r) {
+  const size_t n_opts = r->strike_offsets[r->n_chains];
+  return r->control_variate ? 3 * n_opts + 2 * (size_t)r->n_chains : 2 * n_opts;
+}
+
+// sums -> prices and standard errors.  Plain: mean payoff (HSimulation.tpp:40 divides by
+// n_simulations) and its standard error.  Control variate: c = final value - S has mean 0 (the
+// spot is a martingale, r = 0), so  price = mean(pf) - beta mean(c),  beta = cov(pf, c)/var(c),
+// and the variance shrinks by 1 - corr(pf, c)^2.
+static void finish_prices(const hexo_price_request* r, const double* sums, double* prices,
+                          double* se) {
+  const uint32_t n_opts = r->strike_offsets[r->n_chains];
+  const double n = (double)r->n_paths;
+  const double* sp = sums;
+  const double* sq = sums + n_opts;
+  const double* sx = sums + 2 * (size_t)n_opts;
+  const double* sc = sums + 3 * (size_t)n_opts;
+  const double* sc2 = sc + r->n_chains;
+  for (uint32_t k = 0; k < r->n_chains; ++k) {
+    double mean_c = 0.0, var_c = 0.0;
+    if (r->control_variate) {
+      mean_c = sc[k] / n;
+      var_c = n > 1 ? std::max(0.0, (sc2[k] - n * mean_c * mean_c) / (n - 1)) : 0.0;
+    }
+    for (uint32_t j = r->strike_offsets[k]; j < r->strike_offsets[k + 1]; ++j) {
+      const double mean = sp[j] / n;
+      double var = n > 1 ? std::max(0.0, (sq[j] - n * mean * mean) / (n - 1)) : 0.0;
+      double price = mean;
+      if (r->control_variate && var_c > 0.0) {
+        const double cov = (sx[j] - n * mean * mean_c) / (n - 1);
+        const double beta = cov / var_c;
+        price = mean - beta * mean_c;
+        var = std::max(0.0, var - beta * cov);
+      }
+      prices[j] = price;
+      if (se) se[j] = sqrt(var / n);
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------
 // host: a prepared launch ("plan") of the path kernel for one shard
 // ---------------------------------------------------------------------------
 struct Plan {
   PathArgs args{};
   int payoff = 0, normal_mode = 0, rng_mode = 0;
-  uint32_t grid = 0, block = 0, smem = 0, n_opts = 0;
+  uint32_t grid = 0, block = 0, smem = 0, n_opts = 0, n_sums = 0;
   uint64_t steps_per_path = 0, path_steps = 0, n_streams = 0;
   void* blob = nullptr;       // [segs | strikes | partials | sums]
   double* sums_dev = nullptr; // inside blob unless caller-supplied
@@ -481,16 +525,19 @@ static int plan_create(const hexo_price_request* r, uint64_t stream_begin, uint6
     if (b >= 32 && b <= kMaxBlock && b % 32 == 0) block = b;
   }
   p->rng_mode = r->rng_mode;
-  p->ws = r->rng_mode == HEXO_RNG_SHISHUA && use_ws();
+  const bool plain = r->rng_mode == HEXO_RNG_SHISHUA && !r->control_variate;
+  const uint32_t n_sums = (uint32_t)sums_len(r);
+  p->n_sums = n_sums;
+  p->ws = plain && use_ws();  // the WS / IL experiments carry neither Philox nor the control variate
   const size_t smem_budget = std::min(
       g_ctx.smem_optin, (size_t)(227 * 1024) / (p->ws ? kWsMinBlocks : kMinBlocksPerSM));
   if (p->ws) block = kWsBlock;
-  p->il = r->rng_mode == HEXO_RNG_SHISHUA && !p->ws && use_il();
+  p->il = plain && !p->ws && use_il();
   const int streams_per_block = p->ws ? kWsConsumers : block;  // path-owning threads per block
   auto smem_of = [&](bool acc) {
     return p->ws   ? path_kernel_ws_smem(n_opts, r->normal_mode, acc)
            : p->il ? path_kernel_il_smem(block, n_opts, r->normal_mode, acc)
-                   : path_kernel_smem(block, n_opts, r->normal_mode, acc);
+                   : path_kernel_smem(block, n_sums, r->normal_mode, acc);
   };
   const bool acc_in_smem = smem_of(true) <= smem_budget;
   p->payoff = r->payoff;
@@ -506,10 +553,10 @@ static int plan_create(const hexo_price_request* r, uint64_t stream_begin, uint6
 
   const size_t seg_bytes = segs.size() * sizeof(SegConst);
   const size_t strike_bytes = (size_t)n_opts * sizeof(double);
-  const size_t part_bytes = (size_t)p->grid * 2 * n_opts * sizeof(double);
-  const size_t sums_bytes = (size_t)2 * n_opts * sizeof(double);
+  const size_t part_bytes = (size_t)p->grid * n_sums * sizeof(double);
+  const size_t sums_bytes = (size_t)n_sums * sizeof(double);
   const size_t gacc_bytes =
-      acc_in_smem ? 0 : (size_t)p->grid * (streams_per_block / 32) * 2 * n_opts * sizeof(double);
+      acc_in_smem ? 0 : (size_t)p->grid * (streams_per_block / 32) * n_sums * sizeof(double);
   if (gacc_bytes > ((size_t)8 << 30))
     return fail(HEXO_ERR_TOO_LARGE, "%u options x %u blocks need %zu bytes of accumulators", n_opts,
                 p->grid, gacc_bytes);
@@ -534,6 +581,8 @@ static int plan_create(const hexo_price_request* r, uint64_t stream_begin, uint6
   a.rem_streams = r->n_paths % r->n_streams;
   a.n_seg = r->n_chains;
   a.n_opts = n_opts;
+  a.n_acc = n_sums;
+  a.cv = r->control_variate ? 1u : 0u;
   a.segs = reinterpret_cast<const SegConst*>(base);
   for (size_t k = 0; k < segs.size() && k < (size_t)kInlineSegs; ++k) a.seg_inline[k] = segs[k];
   a.strikes = reinterpret_cast<const double*>(base + off_strikes);
@@ -568,7 +617,7 @@ static int plan_launch(const Plan* p, cudaStream_t st, double* sums_out_dev) {
     kern<<<p->grid, p->block, p->smem, st>>>(p->args);
   }
   HEXO_CUDA(cudaGetLastError());
-  const uint32_t n2 = 2 * p->n_opts;
+  const uint32_t n2 = p->n_sums;
   reduce_partials_kernel<<<(n2 + 127) / 128, 128, 0, st>>>(p->args.partials, p->grid, n2,
                                                             sums_out_dev ? sums_out_dev : p->sums_dev);
   HEXO_CUDA(cudaGetLastError());
@@ -711,7 +760,7 @@ int hexo_gpu_price_shard(const hexo_price_request* req, uint64_t stream_begin,
   rc = plan_launch(&p, st, nullptr);
   if (rc == HEXO_OK) {
     cudaEventRecord(e1, st);
-    cudaError_t e = cudaMemcpyAsync(sums_out, p.sums_dev, (size_t)2 * p.n_opts * sizeof(double),
+    cudaError_t e = cudaMemcpyAsync(sums_out, p.sums_dev, (size_t)p.n_sums * sizeof(double),
                                     cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) rc = fail(HEXO_ERR_CUDA, "path kernel failed: %s", cudaGetErrorString(e));
@@ -734,19 +783,24 @@ int hexo_gpu_price(const hexo_price_request* req, double* prices_out, double* st
   if (rc) return rc;
   hexo_price_request r = *req;
   if (r.n_streams == 0) r.n_streams = default_streams(r.n_paths, 1);
-  const uint32_t n_opts = r.strike_offsets[r.n_chains];
-  std::vector<double> sums(2 * (size_t)n_opts);
+  std::vector<double> sums(sums_len(&r));
   rc = hexo_gpu_price_shard(&r, 0, r.n_streams, sums.data(), stats);
   if (rc) return rc;
-  const double n = (double)r.n_paths;
-  for (uint32_t j = 0; j < n_opts; ++j) {
-    const double mean = sums[j] / n;  // HSimulation.tpp:40 divides by n_simulations
-    prices_out[j] = mean;
-    if (stderr_out) {
-      const double var = n > 1 ? std::max(0.0, (sums[n_opts + j] - n * mean * mean) / (n - 1)) : 0.0;
-      stderr_out[j] = sqrt(var / n);
-    }
-  }
+  finish_prices(&r, sums.data(), prices_out, stderr_out);
+  return HEXO_OK;
+}
+
+size_t hexo_gpu_sums_len(const hexo_price_request* req) {
+  if (!req || !req->strike_offsets || req->n_chains == 0) return 0;
+  return sums_len(req);
+}
+
+int hexo_gpu_finish(const hexo_price_request* req, const double* sums, double* prices_out,
+                    double* stderr_out) {
+  int rc = check_request(req, true);
+  if (rc) return rc;
+  if (!sums || !prices_out) return fail(HEXO_ERR_INVALID_ARGUMENT, "finish: sums / prices_out is NULL");
+  finish_prices(req, sums, prices_out, stderr_out);
   return HEXO_OK;
 }
 
@@ -763,7 +817,7 @@ int hexo_gpu_price_batch(const hexo_price_request* reqs, uint32_t n_reqs, uint32
   for (uint32_t i = 0; i < n_reqs; ++i) {
     const int rc = check_request(&reqs[i], true);
     if (rc) return rc;
-    off[i + 1] = off[i] + 2 * (size_t)reqs[i].strike_offsets[reqs[i].n_chains];
+    off[i + 1] = off[i] + sums_len(&reqs[i]);
   }
   int rc = ensure_context();
   if (rc) return rc;
@@ -820,18 +874,11 @@ int hexo_gpu_price_batch(const hexo_price_request* reqs, uint32_t n_reqs, uint32
   cleanup();
   if (rc) return rc;
   if (e != cudaSuccess) return fail(HEXO_ERR_CUDA, "batch: %s", cudaGetErrorString(e));
+  size_t out_off = 0;
   for (uint32_t i = 0; i < n_reqs; ++i) {
-    const uint32_t n_opts = (uint32_t)((off[i + 1] - off[i]) / 2);
-    const double* sm = sums.data() + off[i];
-    const double n = (double)reqs[i].n_paths;
-    for (uint32_t j = 0; j < n_opts; ++j) {
-      const double mean = sm[j] / n;  // HSimulation.tpp:40
-      prices_out[off[i] / 2 + j] = mean;
-      if (stderr_out) {
-        const double var = n > 1 ? std::max(0.0, (sm[n_opts + j] - n * mean * mean) / (n - 1)) : 0.0;
-        stderr_out[off[i] / 2 + j] = sqrt(var / n);
-      }
-    }
+    finish_prices(&reqs[i], sums.data() + off[i], prices_out + out_off,
+                  stderr_out ? stderr_out + out_off : nullptr);
+    out_off += reqs[i].strike_offsets[reqs[i].n_chains];
     if (stats) fill_stats(plans[i], ms, &stats[i]);  // kernel_ms = the whole batch
   }
   return HEXO_OK;
@@ -878,7 +925,7 @@ int hexo_gpu_price_multi(const hexo_price_request* req, int n_gpus, double* pric
     rc = plan_launch(&plans[g], 0, nullptr);
     cudaEventRecord(ev1[g], 0);
   }
-  std::vector<double> sums(2 * (size_t)n_opts, 0.0), part(2 * (size_t)n_opts);
+  std::vector<double> sums(sums_len(&r), 0.0), part(sums_len(&r));
   float ms_max = 0.f;
   for (int g = 0; g < n_gpus; ++g) {  // then collect
     if (!used[g]) continue;
@@ -903,15 +950,7 @@ int hexo_gpu_price_multi(const hexo_price_request* req, int n_gpus, double* pric
   if (rc) return rc;
   fill_stats(plans[0], ms_max, stats);
   if (stats) stats->kernel_launches = 2 * (uint32_t)n_gpus;
-  const double n = (double)r.n_paths;
-  for (uint32_t j = 0; j < n_opts; ++j) {
-    const double mean = sums[j] / n;
-    prices_out[j] = mean;
-    if (stderr_out) {
-      const double var = n > 1 ? std::max(0.0, (sums[n_opts + j] - n * mean * mean) / (n - 1)) : 0.0;
-      stderr_out[j] = sqrt(var / n);
-    }
-  }
+  finish_prices(&r, sums.data(), prices_out, stderr_out);
   return HEXO_OK;
 }
 

@@ -47,15 +47,20 @@ struct PathArgs {
   uint64_t base_paths;    // every stream runs base_paths paths ...
   uint64_t rem_streams;   // ... and global streams < rem_streams one more
   uint32_t n_seg, n_opts;
+  // Accumulators per warp (= sums per launch).  Plain: [sum pf | sum pf^2] = 2 n_opts.  With the
+  // control variate (cv != 0) the control c = final value - S (zero mean: the spot is a
+  // martingale, r = 0) adds [sum pf c] per option and [sum c | sum c^2] per maturity:
+  // 3 n_opts + 2 n_seg.
+  uint32_t n_acc, cv;
   const SegConst* segs;                // all n_seg segments (device memory)
   SegConst seg_inline[kInlineSegs];    // the first min(n_seg, kInlineSegs) again, in the
                                        // kernel's constant bank: uniform operands, no registers
   const double* strikes;
-  double* partials;  // [gridDim.x][2*n_opts]
+  double* partials;  // [gridDim.x][n_acc]
   uint32_t dev_no_refill;  // development probe (HEXO_NO_REFILL=1): reuse the first generator
                            // round forever, i.e. time the FP64 step loop alone
   double* gacc;      // nullptr: per-warp accumulators in shared memory; else zero-initialised
-                     // [gridDim.x][warps][2*n_opts] in device memory (large option chains,
+                     // [gridDim.x][warps][n_acc] in device memory (large option chains,
                      // where shared-memory accumulators would cost occupancy)
 };
 
@@ -67,13 +72,13 @@ struct PathArgs {
 //   zring  [8][T] pairs (Z_V, Z_X) of the round, float2 (F32 mode) / double2 (F64)
 //   exptab [32]   2^(j/32)
 //   fvbuf  [W][32] final values of a warp at a maturity
-//   acc    [W][2][n_opts] lane-owned payoff sums / sums of squares
-__host__ __device__ inline size_t path_kernel_smem(int block, uint32_t n_opts, int normal_mode,
+//   acc    [W][n_acc] lane-owned payoff sums / sums of squares (/ control-variate sums)
+__host__ __device__ inline size_t path_kernel_smem(int block, uint32_t n_acc, int normal_mode,
                                                    bool acc_in_smem = true) {
   const int warps = block / 32;
   const size_t zbytes = (normal_mode == HEXO_NORMAL_F64 ? 16 : 8) * (size_t)kStepsPerRound * block;
   return zbytes + (size_t)16 * kStepsPerRound * block + 32 * 8 + (size_t)32 * 8 * warps +
-         (acc_in_smem ? (size_t)warps * 2 * n_opts * 8 : 0);
+         (acc_in_smem ? (size_t)warps * n_acc * 8 : 0);
 }
 
 // ---- shared-space accessors (32-bit addresses: no generic-pointer arithmetic
@@ -271,12 +276,14 @@ heston_qe_paths_kernel(const __grid_constant__ PathArgs a) {
   sp += 32 * 8;
   double* fvbuf = reinterpret_cast<double*>(sp) + 32 * warp;
   sp += (size_t)32 * 8 * nwarps;
-  double* acc_all = a.gacc ? a.gacc + (size_t)blockIdx.x * nwarps * 2 * a.n_opts
+  double* acc_all = a.gacc ? a.gacc + (size_t)blockIdx.x * nwarps * a.n_acc
                            : reinterpret_cast<double*>(sp);
-  double* my_sum = acc_all + (size_t)warp * 2 * a.n_opts;  // lane-owned slots
+  double* my_sum = acc_all + (size_t)warp * a.n_acc;  // lane-owned slots
   double* my_sq = my_sum + a.n_opts;
+  double* my_cross = my_sq + a.n_opts;    // cv only: sum pf c per option ...
+  double* my_ctl = my_cross + a.n_opts;   // ... and sum c, sum c^2 per maturity (lane 0)
   if (!a.gacc)
-    for (uint32_t j = lane; j < 2 * a.n_opts; j += 32) my_sum[j] = 0.0;
+    for (uint32_t j = lane; j < a.n_acc; j += 32) my_sum[j] = 0.0;
   exp_table_init(exptab, tid, T);
 
   const uint64_t slot = (uint64_t)blockIdx.x * T + tid;
@@ -420,26 +427,59 @@ heston_qe_paths_kernel(const __grid_constant__ PathArgs a) {
       __syncwarp();
       // final_payoff for every strike of this chain (HSimulation.tpp:39-40): lane
       // l owns strikes l, l+32, ... and walks the warp's 32 final values.
-      for (uint32_t j = lane; j < g.n_strikes; j += 32) {
-        const double K = __ldg(a.strikes + g.first_opt + j);
-        double s = 0.0, q = 0.0;
+      if (!a.cv) {
+        for (uint32_t j = lane; j < g.n_strikes; j += 32) {
+          const double K = __ldg(a.strikes + g.first_opt + j);
+          double s = 0.0, q = 0.0;
 #pragma unroll 8
-        for (int l = 0; l < 32; ++l) {
-          if ((amask >> l) & 1u) {
-            const double pf = fmax(fvbuf[l] - K, 0.0);
-            s += pf;
-            q = fma(pf, pf, q);
+          for (int l = 0; l < 32; ++l) {
+            if ((amask >> l) & 1u) {
+              const double pf = fmax(fvbuf[l] - K, 0.0);
+              s += pf;
+              q = fma(pf, pf, q);
+            }
           }
+          my_sum[g.first_opt + j] += s;
+          my_sq[g.first_opt + j] += q;
         }
-        my_sum[g.first_opt + j] += s;
-        my_sq[g.first_opt + j] += q;
+      } else {
+        // control variate: the same walk also collects sum pf c, c = final value - S
+        for (uint32_t j = lane; j < g.n_strikes; j += 32) {
+          const double K = __ldg(a.strikes + g.first_opt + j);
+          double s = 0.0, q = 0.0, x = 0.0;
+#pragma unroll 8
+          for (int l = 0; l < 32; ++l) {
+            if ((amask >> l) & 1u) {
+              const double f = fvbuf[l];
+              const double pf = fmax(f - K, 0.0);
+              s += pf;
+              q = fma(pf, pf, q);
+              x = fma(pf, f - a.S, x);
+            }
+          }
+          my_sum[g.first_opt + j] += s;
+          my_sq[g.first_opt + j] += q;
+          my_cross[g.first_opt + j] += x;
+        }
+        if (lane == 0) {  // sum c, sum c^2 of this maturity, in lane order
+          double c1 = 0.0, c2 = 0.0;
+          for (int l = 0; l < 32; ++l) {
+            if ((amask >> l) & 1u) {
+              const double c = fvbuf[l] - a.S;
+              c1 += c;
+              c2 = fma(c, c, c2);
+            }
+          }
+          my_ctl[k] += c1;
+          my_ctl[a.n_seg + k] += c2;
+        }
       }
     }
   }
 
   // warps -> block partial, fixed order
   __syncthreads();
-  const uint32_t n2 = 2 * a.n_opts;
+  const uint32_t n2 = a.n_acc;
   for (uint32_t j = tid; j < n2; j += T) {
     double s = 0.0;
     for (int w = 0; w < nwarps; ++w) s += acc_all[(size_t)w * n2 + j];

@@ -42,6 +42,7 @@ _NORMAL_MODES = {"f32": _lib.NORMAL_F32, "as-built": _lib.NORMAL_F32, "f64": _li
                  _lib.NORMAL_F32: _lib.NORMAL_F32, _lib.NORMAL_F64: _lib.NORMAL_F64}
 _RNG_MODES = {"shishua": 0, "philox": 1, 0: 0, 1: 1}   # hexo_rng_mode
 _GRID_MODES = {"reference": 0, "exact": 1, 0: 0, 1: 1}  # hexo_schedule_mode
+_CV_MODES = {None: 0, "none": 0, "underlying": 1, 0: 0, 1: 1}  # hexo_control_variate
 
 
 @dataclass
@@ -63,7 +64,7 @@ class _Request:
 
     def __init__(self, scheme, p: HParams, S: float, all_chains: Sequence[OptionsChain],
                  n_simulations: int, n_opts: Optional[int], steps: int, seed: int, normal_mode,
-                 n_streams: int, rng="shishua", time_grid="reference"):
+                 n_streams: int, rng="shishua", time_grid="reference", control_variate=None):
         if isinstance(scheme, type) and hasattr(scheme, "payoff"):
             scheme = HQEAnderson(scheme)
         self.expiries, self.offsets, self.strikes = flatten_chains(all_chains)
@@ -77,42 +78,51 @@ class _Request:
             raise ValueError(f"rng must be 'shishua' or 'philox', got {rng!r}")
         if time_grid not in _GRID_MODES:
             raise ValueError(f"time_grid must be 'reference' or 'exact', got {time_grid!r}")
+        if control_variate not in _CV_MODES:
+            raise ValueError(f"control_variate must be None or 'underlying', got {control_variate!r}")
         self.req = _lib.HexoPriceRequest(
             _lib.HexoHParams(*p.as_tuple()), float(S), scheme.payoff, len(self.expiries),
             self.expiries.ctypes.data_as(_lib.c_double_p),
             self.offsets.ctypes.data_as(_lib.c_uint32_p),
             self.strikes.ctypes.data_as(_lib.c_double_p),
             int(n_simulations), int(steps), int(seed), _NORMAL_MODES[normal_mode],
-            _RNG_MODES[rng], int(n_streams), _GRID_MODES[time_grid], 0)
+            _RNG_MODES[rng], int(n_streams), _GRID_MODES[time_grid], _CV_MODES[control_variate])
+        self.n_sums = 3 * self.n_opts + 2 * len(self.expiries) if self.req.control_variate \
+            else 2 * self.n_opts
 
 
-def _finish(sums: np.ndarray, n_paths: int, n_opts: int):
-    n = float(n_paths)
-    mean = sums[:n_opts] / n                      # HSimulation.tpp:40 divides by n_simulations
-    if n_paths > 1:
-        var = np.maximum(0.0, (sums[n_opts:] - n * mean * mean) / (n - 1.0))
-    else:
-        var = np.zeros(n_opts)
-    return mean, np.sqrt(var / n)
+def _finish(rq: "_Request", sums: np.ndarray):
+    """sums -> (prices, standard errors) with the library's own host routine (hexo_gpu_finish):
+    the mean payoff (HSimulation.tpp:40 divides by n_simulations), or the control-variate
+    estimate when the request asks for one."""
+    lib = _lib.load()
+    sums = np.ascontiguousarray(sums, dtype=np.float64)
+    assert sums.size == rq.n_sums == lib.hexo_gpu_sums_len(C.byref(rq.req))
+    prices, se = np.zeros(rq.n_opts), np.zeros(rq.n_opts)
+    _lib.check(lib.hexo_gpu_finish(C.byref(rq.req), sums.ctypes.data_as(_lib.c_double_p),
+                                   prices.ctypes.data_as(_lib.c_double_p),
+                                   se.ctypes.data_as(_lib.c_double_p)))
+    return prices, se
 
 
 def price_full(scheme, p: HParams, S: float, all_chains: Sequence[OptionsChain],
                n_simulations: int, n_opts: Optional[int], steps: int, *, seed: int = 1,
                normal_mode="f32", n_streams: int = 0, rng="shishua",
-               time_grid="reference", device: Optional[int] = None) -> PriceResult:
+               time_grid="reference", control_variate=None,
+               device: Optional[int] = None) -> PriceResult:
     """price<Scheme>() on one GPU, returning prices, standard errors and launch statistics."""
     lib = _lib.load()
     if device is not None:
         _lib.check(lib.hexo_gpu_init(int(device)))
     rq = _Request(scheme, p, S, all_chains, n_simulations, n_opts, steps, seed, normal_mode,
-                  n_streams, rng, time_grid)
+                  n_streams, rng, time_grid, control_variate)
     if rq.req.n_streams == 0:
         rq.req.n_streams = lib.hexo_gpu_default_streams(rq.req.n_paths, rq.n_opts, 1)
-    sums = np.zeros(2 * rq.n_opts, dtype=np.float64)
+    sums = np.zeros(rq.n_sums, dtype=np.float64)
     stats = _lib.HexoGpuStats()
     _lib.check(lib.hexo_gpu_price_shard(C.byref(rq.req), 0, rq.req.n_streams,
                                         sums.ctypes.data_as(_lib.c_double_p), C.byref(stats)))
-    mean, se = _finish(sums, int(n_simulations), rq.n_opts)
+    mean, se = _finish(rq, sums)
     return PriceResult(mean, se, sums, int(n_simulations), int(stats.n_streams),
                        int(stats.steps_per_path), int(stats.path_steps), float(stats.kernel_ms),
                        int(stats.grid), int(stats.block))
@@ -121,12 +131,12 @@ def price_full(scheme, p: HParams, S: float, all_chains: Sequence[OptionsChain],
 def price_multi(scheme, p: HParams, S: float, all_chains: Sequence[OptionsChain],
                 n_simulations: int, n_opts: Optional[int], steps: int, *, n_gpus: int = 0,
                 seed: int = 1, normal_mode="f32", n_streams: int = 0, rng="shishua",
-                time_grid="reference"):
+                time_grid="reference", control_variate=None):
     """price<Scheme>() spread over several GPUs of THIS process (hexo_gpu_price_multi); returns
     (prices, stderr).  n_gpus = 0 uses every visible device."""
     lib = _lib.load()
     rq = _Request(scheme, p, S, all_chains, n_simulations, n_opts, steps, seed, normal_mode,
-                  n_streams, rng, time_grid)
+                  n_streams, rng, time_grid, control_variate)
     prices, se = np.zeros(rq.n_opts), np.zeros(rq.n_opts)
     _lib.check(lib.hexo_gpu_price_multi(C.byref(rq.req), int(n_gpus),
                                         prices.ctypes.data_as(_lib.c_double_p),
@@ -137,7 +147,7 @@ def price_multi(scheme, p: HParams, S: float, all_chains: Sequence[OptionsChain]
 def price_batch(scheme, params: Sequence[HParams], S: float, all_chains: Sequence[OptionsChain],
                 n_simulations: int, n_opts: Optional[int], steps: int, *, seeds=1,
                 normal_mode="f32", n_streams: int = 0, rng="shishua", time_grid="reference",
-                n_lanes: int = 0):
+                control_variate=None, n_lanes: int = 0):
     """price<Scheme>() of the same chains for MANY parameter sets in one submission
     (hexo_gpu_price_batch): the shape of Monte-Carlo pricing inside a calibration loop.  `seeds`
     is one seed for all jobs (common random numbers) or one per parameter set.  Returns
@@ -150,7 +160,7 @@ def price_batch(scheme, params: Sequence[HParams], S: float, all_chains: Sequenc
     if len(seeds) != len(params):
         raise ValueError("one seed per parameter set")
     rqs = [_Request(scheme, p, S, all_chains, n_simulations, n_opts, steps, sd, normal_mode,
-                    n_streams, rng, time_grid) for p, sd in zip(params, seeds)]
+                    n_streams, rng, time_grid, control_variate) for p, sd in zip(params, seeds)]
     arr = (_lib.HexoPriceRequest * len(rqs))(*[r.req for r in rqs])
     n = rqs[0].n_opts
     prices, se = np.zeros((len(rqs), n)), np.zeros((len(rqs), n))
@@ -177,12 +187,13 @@ def shard_range(n_streams: int, rank: int, world_size: int):
 def price_distributed(scheme, p: HParams, S: float, all_chains: Sequence[OptionsChain],
                       n_simulations: int, n_opts: Optional[int], steps: int, *, seed: int = 1,
                       normal_mode="f32", n_streams: int = 0, rng="shishua",
-                      time_grid="reference", group=None,
+                      time_grid="reference", control_variate=None, group=None,
                       _shard_sums=None) -> PriceResult:
     """price<Scheme>() sharded over the ranks of a torch.distributed group.
 
     Every rank runs a disjoint range of RNG streams on its own GPU and the
-    2*n_opts payoff sums are combined with ONE all-reduce (NCCL over NVLink when
+    payoff sums (2*n_opts doubles, a few more with a control variate) are combined with ONE
+    all-reduce (NCCL over NVLink when
     the group's backend is nccl).  All ranks return the same prices.  `_shard_sums`
     (tests only) replaces the GPU shard computation so the sharding logic can be
     exercised with gloo on CPU.
@@ -192,7 +203,7 @@ def price_distributed(scheme, p: HParams, S: float, all_chains: Sequence[Options
 
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     rq = _Request(scheme, p, S, all_chains, n_simulations, n_opts, steps, seed, normal_mode,
-                  n_streams, rng, time_grid)
+                  n_streams, rng, time_grid, control_variate)
     stats = _lib.HexoGpuStats()
     if _shard_sums is None:
         lib = _lib.load()
@@ -201,7 +212,7 @@ def price_distributed(scheme, p: HParams, S: float, all_chains: Sequence[Options
         if rq.req.n_streams == 0:
             rq.req.n_streams = lib.hexo_gpu_default_streams(rq.req.n_paths, rq.n_opts, world)
         begin, count = shard_range(rq.req.n_streams, rank, world)
-        sums_t = torch.zeros(2 * rq.n_opts, dtype=torch.float64, device=f"cuda:{dev}")
+        sums_t = torch.zeros(rq.n_sums, dtype=torch.float64, device=f"cuda:{dev}")
         if count > 0:
             stream = torch.cuda.current_stream().cuda_stream
             _lib.check(lib.hexo_gpu_price_shard_device(
@@ -214,7 +225,7 @@ def price_distributed(scheme, p: HParams, S: float, all_chains: Sequence[Options
         sums_t = torch.from_numpy(np.asarray(_shard_sums(rq, begin, count), dtype=np.float64).copy())
     dist.all_reduce(sums_t, op=dist.ReduceOp.SUM, group=group)
     sums = sums_t.cpu().numpy()
-    mean, se = _finish(sums, int(n_simulations), rq.n_opts)
+    mean, se = _finish(rq, sums)
     return PriceResult(mean, se, sums, int(n_simulations), int(rq.req.n_streams),
                        int(stats.steps_per_path), int(n_simulations) * int(steps), 0.0,
                        int(stats.grid), int(stats.block))

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define HEXO_GPU_ABI_VERSION 2 /* 2: rng_mode, schedule_mode in hexo_price_request */
+#define HEXO_GPU_ABI_VERSION 2 /* 2: rng_mode, schedule_mode, control_variate in the request */
 
 typedef enum {
   HEXO_OK = 0,
@@ -66,6 +66,15 @@ typedef enum { HEXO_RNG_SHISHUA = 0, HEXO_RNG_PHILOX = 1 } hexo_rng_mode;
  * is the full trapezoid rule and the European payoff reads X at the last step. */
 typedef enum { HEXO_SCHEDULE_REFERENCE = 0, HEXO_SCHEDULE_EXACT = 1 } hexo_schedule_mode;
 
+/* Control variate (the reference only suggests one, src/inc/HSimulation.h:51).  UNDERLYING uses
+ * what the path already holds: c = final value - S, i.e. the arithmetic average (Asian) or the
+ * terminal spot (European) minus the initial spot.  E[c] = 0 because the model has no drift
+ * (HSimulation.tpp:75-80), so  price = mean(payoff) - beta mean(c)  with
+ * beta = cov(payoff, c) / var(c) estimated from the same paths; the standard error shrinks by
+ * sqrt(1 - corr(payoff, c)^2).  The sums gain [sum payoff c] per option and [sum c | sum c^2]
+ * per maturity (hexo_gpu_sums_len). */
+typedef enum { HEXO_CV_NONE = 0, HEXO_CV_UNDERLYING = 1 } hexo_control_variate;
+
 /* HParams, src/inc/HDistribution.h:9-24 -- same field order, same meaning */
 typedef struct {
   double v_0;   /* initial variance            */
@@ -99,7 +108,7 @@ typedef struct {
                                   /* sums do not depend on how streams are      */
                                   /* sharded over GPUs.                         */
   int32_t schedule_mode;          /* hexo_schedule_mode; 0 = the reference's    */
-  int32_t reserved;               /* must be 0                                  */
+  int32_t control_variate;        /* hexo_control_variate; 0 = none             */
 } hexo_price_request;
 
 typedef struct {
@@ -154,6 +163,14 @@ int hexo_gpu_price(const hexo_price_request *req, double *prices_out, double *st
 int hexo_gpu_price_batch(const hexo_price_request *reqs, uint32_t n_reqs, uint32_t n_lanes,
                          double *prices_out, double *stderr_out, hexo_gpu_stats *stats);
 
+/* Number of doubles a shard's sums hold for this request: 2 n_opts ([sum payoff | sum payoff^2]),
+ * or 3 n_opts + 2 n_chains with a control variate ([.. | sum payoff c | sum c | sum c^2]).
+ * Sums of disjoint stream ranges add up; hexo_gpu_finish turns the total into prices and
+ * standard errors exactly as hexo_gpu_price does (host only, no GPU). */
+size_t hexo_gpu_sums_len(const hexo_price_request *req);
+int hexo_gpu_finish(const hexo_price_request *req, const double *sums, double *prices_out,
+                    double *stderr_out);
+
 /* The same call spread over the first n_gpus devices of this process (n_gpus <= 0: all
  * visible devices): the single-process counterpart of the one-rank-per-GPU path, for callers
  * like the reference's CLI.  Streams are split over devices like ranks split them; the sums
@@ -164,13 +181,14 @@ int hexo_gpu_price_multi(const hexo_price_request *req, int n_gpus, double *pric
 /* The same path for one shard of the job: streams [stream_begin,
  * stream_begin+stream_count) of req->n_streams (which must be non-zero here).
  * sums_out[0..n_opts) = sum of payoffs, sums_out[n_opts..2 n_opts) = sum of
- * squared payoffs over this shard's paths; summing shards (e.g. by an
- * all-reduce) and dividing by n_paths gives the price. */
+ * squared payoffs over this shard's paths (hexo_gpu_sums_len(req) doubles in all:
+ * a control variate appends its own sums); summing shards (e.g. by an all-reduce)
+ * and dividing by n_paths gives the price -- hexo_gpu_finish does exactly that. */
 int hexo_gpu_price_shard(const hexo_price_request *req, uint64_t stream_begin,
                          uint64_t stream_count, double *sums_out, hexo_gpu_stats *stats);
 
 /* Same, asynchronous: enqueues on `cuda_stream` (a cudaStream_t, 0 = default)
- * and leaves the 2*n_opts sums in DEVICE memory at sums_device, ready for an
+ * and leaves the hexo_gpu_sums_len(req) sums in DEVICE memory at sums_device, ready for an
  * NCCL all-reduce on the same stream.  No host synchronisation. */
 int hexo_gpu_price_shard_device(const hexo_price_request *req, uint64_t stream_begin,
                                 uint64_t stream_count, double *sums_device, void *cuda_stream,

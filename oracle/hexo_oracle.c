@@ -433,6 +433,8 @@ typedef struct {
   const oracle_contract *c;
   double *prices, *sum, *sumsq;
   double n_sims;
+  /* control variate c = final value - S (include/hexo_gpu.h, HEXO_CV_UNDERLYING); may be NULL */
+  double *cross, *ctl, *ctl2;
 } sum_sink;
 
 static void pay_sums(void *ctx, uint32_t chain, const policy *o) {
@@ -442,7 +444,10 @@ static void pay_sums(void *ctx, uint32_t chain, const policy *o) {
     if (k->prices) k->prices[j] += pf / k->n_sims;                  /* :40 */
     if (k->sum) k->sum[j] += pf;
     if (k->sumsq) k->sumsq[j] += pf * pf;
+    if (k->cross) k->cross[j] += pf * (o->final_value - k->c->S);
   }
+  if (k->ctl) k->ctl[chain] += o->final_value - k->c->S;
+  if (k->ctl2) k->ctl2[chain] += (o->final_value - k->c->S) * (o->final_value - k->c->S);
 }
 
 typedef struct {
@@ -474,7 +479,7 @@ int oracle_price_ref(const oracle_contract *c, unsigned int n_sims, unsigned int
   if (prices) memset(prices, 0, n_opts * sizeof(double));           /* :22 */
   if (sum) memset(sum, 0, n_opts * sizeof(double));
   if (sumsq) memset(sumsq, 0, n_opts * sizeof(double));
-  sum_sink sink = {c, prices, sum, sumsq, (double)n_sims};
+  sum_sink sink = {c, prices, sum, sumsq, (double)n_sims, NULL, NULL, NULL};
   for (unsigned int tid = 0; tid < nthreads; ++tid) {               /* :23 */
     const unsigned int local_sims = n_sims / nthreads;              /* :27 */
     oracle_rng *rng = oracle_rng_new(rand_buf_size, 1u << tid, normal_mode); /* :28 */
@@ -503,7 +508,7 @@ int oracle_price_stream_rng(const oracle_contract *c, int rng_mode, uint64_t see
   const uint32_t n_opts = c->strike_offsets[c->n_chains];
   if (sum) memset(sum, 0, n_opts * sizeof(double));
   if (sumsq) memset(sumsq, 0, n_opts * sizeof(double));
-  sum_sink sink = {c, NULL, sum, sumsq, (double)n_paths};
+  sum_sink sink = {c, NULL, sum, sumsq, (double)n_paths, NULL, NULL, NULL};
   const uint64_t base = n_paths / n_streams_total, rem = n_paths % n_streams_total;
   for (uint64_t s = stream_begin; s < stream_begin + stream_count; ++s) {
     stream_ctx sc;
@@ -562,7 +567,7 @@ int oracle_price_stream_exact(const oracle_contract *c, int rng_mode, uint64_t s
   const uint32_t n_opts = c->strike_offsets[c->n_chains];
   if (sum) memset(sum, 0, n_opts * sizeof(double));
   if (sumsq) memset(sumsq, 0, n_opts * sizeof(double));
-  sum_sink sink = {c, NULL, sum, sumsq, (double)n_paths};
+  sum_sink sink = {c, NULL, sum, sumsq, (double)n_paths, NULL, NULL, NULL};
   const uint64_t base = n_paths / n_streams_total, rem = n_paths % n_streams_total;
   for (uint64_t s = stream_begin; s < stream_begin + stream_count; ++s) {
     stream_ctx sc;
@@ -577,6 +582,42 @@ int oracle_price_stream_exact(const oracle_contract *c, int rng_mode, uint64_t s
     draw_src d = {strsrc_gv, strsrc_uv, strsrc_gx, strsrc_end, &sc};
     const uint64_t my_paths = base + (s < rem ? 1 : 0);
     for (uint64_t i = 0; i < my_paths; ++i) simulate_path_exact(c, &d, pay_sums, &sink);
+  }
+  return 0;
+}
+
+/* Stream pricer with the control-variate sums (include/hexo_gpu.h, HEXO_CV_UNDERLYING):
+ * out = [sum pf | sum pf^2 | sum pf c] per option, then [sum c | sum c^2] per maturity,
+ * c = final value - S.  exact_grid selects the corrected time grid. */
+int oracle_price_stream_cv(const oracle_contract *c, int rng_mode, int exact_grid, uint64_t seed,
+                           uint64_t n_paths, uint64_t n_streams_total, uint64_t stream_begin,
+                           uint64_t stream_count, int normal_mode, double *out) {
+  int rc = check_contract(c);
+  if (rc) return rc;
+  if (n_streams_total == 0 || stream_begin + stream_count > n_streams_total || !out) return -1;
+  const uint32_t n_opts = c->strike_offsets[c->n_chains];
+  memset(out, 0, (3 * (size_t)n_opts + 2 * (size_t)c->n_chains) * sizeof(double));
+  sum_sink sink = {c, NULL, out, out + n_opts, (double)n_paths, out + 2 * (size_t)n_opts,
+                   out + 3 * (size_t)n_opts, out + 3 * (size_t)n_opts + c->n_chains};
+  const uint64_t base = n_paths / n_streams_total, rem = n_paths % n_streams_total;
+  for (uint64_t s = stream_begin; s < stream_begin + stream_count; ++s) {
+    stream_ctx sc;
+    memset(&sc, 0, sizeof(sc));
+    uint64_t sd[4] = {seed, s, 0, 0};
+    prng_init(&sc.s, sd);
+    sc.pos = 16;
+    sc.normal_mode = normal_mode;
+    sc.rng_mode = rng_mode;
+    sc.seed = seed;
+    sc.stream = s;
+    draw_src d = {strsrc_gv, strsrc_uv, strsrc_gx, strsrc_end, &sc};
+    const uint64_t my_paths = base + (s < rem ? 1 : 0);
+    for (uint64_t i = 0; i < my_paths; ++i) {
+      if (exact_grid)
+        simulate_path_exact(c, &d, pay_sums, &sink);
+      else
+        simulate_path(c, &d, 0, pay_sums, &sink);
+    }
   }
   return 0;
 }

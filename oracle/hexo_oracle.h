@@ -107,6 +107,14 @@ int oracle_price_stream_exact(const oracle_contract *c, int rng_mode, uint64_t s
                               uint64_t n_paths, uint64_t n_streams_total, uint64_t stream_begin,
                               uint64_t stream_count, int normal_mode, double *sum, double *sumsq);
 
+/* Stream pricer with the sums of the control variate c = final value - S (NOT in the
+ * reference, which only suggests one at src/inc/HSimulation.h:51): out holds
+ * [sum pf | sum pf^2 | sum pf c] per option, then [sum c | sum c^2] per maturity
+ * (3 n_opts + 2 n_chains doubles). */
+int oracle_price_stream_cv(const oracle_contract *c, int rng_mode, int exact_grid, uint64_t seed,
+                           uint64_t n_paths, uint64_t n_streams_total, uint64_t stream_begin,
+                           uint64_t stream_count, int normal_mode, double *out);
+
 /* ---- tape replay ------------------------------------------------------------
  * tape[path][step][3] = {Z_V, U_V, Z_X}; the stepper takes Z_V or U_V according
  * to its branch.  finals[path][chain] receives the policy's final_value (Asian

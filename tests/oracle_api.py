@@ -74,6 +74,9 @@ def oracle() -> C.CDLL:
                                               C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64,
                                               C.c_int, dp, dp]
         o.oracle_price_stream_exact.argtypes = o.oracle_price_stream_rng.argtypes
+        o.oracle_price_stream_cv.argtypes = [C.POINTER(OracleContract), C.c_int, C.c_int,
+                                             C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64,
+                                             C.c_uint64, C.c_int, dp]
         o.oracle_philox4x32_10.argtypes = [C.POINTER(C.c_uint32)] * 3
         o.oracle_philox4x32_10.restype = None
         o.oracle_replay.argtypes = [C.POINTER(OracleContract), dp, C.c_uint64, C.c_uint32, dp]
@@ -142,6 +145,18 @@ class Contract:
                 sm.ctypes.data_as(dp), sq.ctypes.data_as(dp))
         assert rc == 0, rc
         return sm, sq
+
+    def price_stream_cv(self, seed, n_paths, n_streams, begin=0, count=None,
+                        normal_mode=NORMAL_F32, rng_mode=0, exact_grid=False):
+        """All sums of a control-variate request: [pf | pf^2 | pf c] per option, [c | c^2] per
+        maturity, c = final value - S."""
+        count = n_streams - begin if count is None else count
+        out = np.zeros(3 * self.n_opts + 2 * len(self.expiries))
+        rc = oracle().oracle_price_stream_cv(C.byref(self.c), rng_mode, int(exact_grid), seed,
+                                             n_paths, n_streams, begin, count, normal_mode,
+                                             out.ctypes.data_as(dp))
+        assert rc == 0, rc
+        return out
 
     def replay(self, tape):
         tape = np.ascontiguousarray(tape, dtype=np.float64)
