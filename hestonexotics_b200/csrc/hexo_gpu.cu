@@ -426,31 +426,37 @@ struct Plan {
   void* blob = nullptr;       // [segs | strikes | partials | sums]
   double* sums_dev = nullptr; // inside blob unless caller-supplied
   size_t gacc_bytes = 0;
+  bool cv = false;  // control-variate sums (template parameter CV of the path kernel)
   bool ws = false;  // warp-specialised kernel (path_kernel_ws.cuh)
   bool il = false;  // interleaved look-ahead kernel (path_kernel_il.cuh)
 };
 
 typedef void (*PathKernel)(const PathArgs);
-template <int SEGS, class Gen>
+template <int SEGS, class Gen, bool CV>
 static PathKernel pick_kernel_t(int payoff, int normal_mode) {
   if (payoff == HEXO_PAYOFF_ASIAN)
     return normal_mode == HEXO_NORMAL_F64
-               ? heston_qe_paths_kernel<HEXO_PAYOFF_ASIAN, 1, SEGS, Gen>
-               : heston_qe_paths_kernel<HEXO_PAYOFF_ASIAN, 0, SEGS, Gen>;
+               ? heston_qe_paths_kernel<HEXO_PAYOFF_ASIAN, 1, SEGS, Gen, CV>
+               : heston_qe_paths_kernel<HEXO_PAYOFF_ASIAN, 0, SEGS, Gen, CV>;
   return normal_mode == HEXO_NORMAL_F64
-             ? heston_qe_paths_kernel<HEXO_PAYOFF_EUROPEAN, 1, SEGS, Gen>
-             : heston_qe_paths_kernel<HEXO_PAYOFF_EUROPEAN, 0, SEGS, Gen>;
+             ? heston_qe_paths_kernel<HEXO_PAYOFF_EUROPEAN, 1, SEGS, Gen, CV>
+             : heston_qe_paths_kernel<HEXO_PAYOFF_EUROPEAN, 0, SEGS, Gen, CV>;
 }
-template <class Gen>
+template <class Gen, bool CV>
 static PathKernel pick_kernel_g(int payoff, int normal_mode, uint32_t n_seg) {
-  return n_seg == 1                       ? pick_kernel_t<kSegsSingle, Gen>(payoff, normal_mode)
-         : n_seg <= (uint32_t)kInlineSegs ? pick_kernel_t<kSegsInline, Gen>(payoff, normal_mode)
-                                          : pick_kernel_t<kSegsGlobal, Gen>(payoff, normal_mode);
+  return n_seg == 1 ? pick_kernel_t<kSegsSingle, Gen, CV>(payoff, normal_mode)
+         : n_seg <= (uint32_t)kInlineSegs
+             ? pick_kernel_t<kSegsInline, Gen, CV>(payoff, normal_mode)
+             : pick_kernel_t<kSegsGlobal, Gen, CV>(payoff, normal_mode);
 }
-// Philox mode: only the default kernel shape carries it (not the WS / IL experiments)
-static PathKernel pick_kernel(int payoff, int normal_mode, uint32_t n_seg, int rng_mode = 0) {
-  return rng_mode == HEXO_RNG_PHILOX ? pick_kernel_g<PhiloxGen>(payoff, normal_mode, n_seg)
-                                     : pick_kernel_g<Shishua>(payoff, normal_mode, n_seg);
+// Philox and the control variate: only the default kernel shape carries them (not WS / IL)
+static PathKernel pick_kernel(int payoff, int normal_mode, uint32_t n_seg, int rng_mode = 0,
+                              bool cv = false) {
+  if (rng_mode == HEXO_RNG_PHILOX)
+    return cv ? pick_kernel_g<PhiloxGen, true>(payoff, normal_mode, n_seg)
+              : pick_kernel_g<PhiloxGen, false>(payoff, normal_mode, n_seg);
+  return cv ? pick_kernel_g<Shishua, true>(payoff, normal_mode, n_seg)
+            : pick_kernel_g<Shishua, false>(payoff, normal_mode, n_seg);
 }
 
 typedef void (*PathKernelWs)(const PathArgs, const uint32_t);
@@ -581,8 +587,7 @@ static int plan_create(const hexo_price_request* r, uint64_t stream_begin, uint6
   a.rem_streams = r->n_paths % r->n_streams;
   a.n_seg = r->n_chains;
   a.n_opts = n_opts;
-  a.n_acc = n_sums;
-  a.cv = r->control_variate ? 1u : 0u;
+  p->cv = r->control_variate != HEXO_CV_NONE;
   a.segs = reinterpret_cast<const SegConst*>(base);
   for (size_t k = 0; k < segs.size() && k < (size_t)kInlineSegs; ++k) a.seg_inline[k] = segs[k];
   a.strikes = reinterpret_cast<const double*>(base + off_strikes);
@@ -599,7 +604,8 @@ static int plan_create(const hexo_price_request* r, uint64_t stream_begin, uint6
     HEXO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem));
   } else {
     PathKernel kern = p->il ? pick_il_kernel(p->payoff, p->normal_mode, p->args.n_seg)
-                            : pick_kernel(p->payoff, p->normal_mode, p->args.n_seg, p->rng_mode);
+                            : pick_kernel(p->payoff, p->normal_mode, p->args.n_seg, p->rng_mode,
+                                           p->cv);
     HEXO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem));
   }
   return HEXO_OK;
@@ -613,7 +619,8 @@ static int plan_launch(const Plan* p, cudaStream_t st, double* sums_out_dev) {
     kern<<<p->grid, p->block, p->smem, st>>>(p->args, (uint32_t)p->steps_per_path);
   } else {
     PathKernel kern = p->il ? pick_il_kernel(p->payoff, p->normal_mode, p->args.n_seg)
-                            : pick_kernel(p->payoff, p->normal_mode, p->args.n_seg, p->rng_mode);
+                            : pick_kernel(p->payoff, p->normal_mode, p->args.n_seg, p->rng_mode,
+                                           p->cv);
     kern<<<p->grid, p->block, p->smem, st>>>(p->args);
   }
   HEXO_CUDA(cudaGetLastError());

@@ -47,15 +47,14 @@ struct PathArgs {
   uint64_t base_paths;    // every stream runs base_paths paths ...
   uint64_t rem_streams;   // ... and global streams < rem_streams one more
   uint32_t n_seg, n_opts;
-  // Accumulators per warp (= sums per launch).  Plain: [sum pf | sum pf^2] = 2 n_opts.  With the
-  // control variate (cv != 0) the control c = final value - S (zero mean: the spot is a
-  // martingale, r = 0) adds [sum pf c] per option and [sum c | sum c^2] per maturity:
-  // 3 n_opts + 2 n_seg.
-  uint32_t n_acc, cv;
   const SegConst* segs;                // all n_seg segments (device memory)
   SegConst seg_inline[kInlineSegs];    // the first min(n_seg, kInlineSegs) again, in the
                                        // kernel's constant bank: uniform operands, no registers
   const double* strikes;
+  // Accumulators per warp (= sums per launch), n_acc.  Plain: [sum pf | sum pf^2] = 2 n_opts.
+  // With the control variate (template parameter CV) the control c = final value - S (zero
+  // mean: the spot is a martingale, r = 0) adds [sum pf c] per option and [sum c | sum c^2] per
+  // maturity: 3 n_opts + 2 n_seg.
   double* partials;  // [gridDim.x][n_acc]
   uint32_t dev_no_refill;  // development probe (HEXO_NO_REFILL=1): reuse the first generator
                            // round forever, i.e. time the FP64 step loop alone
@@ -247,6 +246,45 @@ struct ZRing<HEXO_NORMAL_F64> {
   }
 };
 
+// Payoff accumulation of one maturity with the control variate c = final value - S: the walk
+// over the warp's 32 final values also collects sum pf c per strike, and lane 0 adds sum c and
+// sum c^2 of the maturity (in lane order).  Once per path and maturity, so it is kept out of line:
+// the step loop's register allocation must not pay for it.
+__device__ __forceinline__ void accumulate_with_control(const double* fvbuf, unsigned amask, int lane,
+                                                     const double* strikes, uint32_t n_strikes,
+                                                     double S, double* sum, double* sq,
+                                                     double* cross, double* ctl, double* ctl2) {
+  for (uint32_t j = lane; j < n_strikes; j += 32) {
+    const double K = __ldg(strikes + j);
+    double s = 0.0, q = 0.0, x = 0.0;
+#pragma unroll 8
+    for (int l = 0; l < 32; ++l) {
+      if ((amask >> l) & 1u) {
+        const double f = fvbuf[l];
+        const double pf = fmax(f - K, 0.0);
+        s += pf;
+        q = fma(pf, pf, q);
+        x = fma(pf, f - S, x);
+      }
+    }
+    sum[j] += s;
+    sq[j] += q;
+    cross[j] += x;
+  }
+  if (lane == 0) {
+    double c1 = 0.0, c2 = 0.0;
+    for (int l = 0; l < 32; ++l) {
+      if ((amask >> l) & 1u) {
+        const double c = fvbuf[l] - S;
+        c1 += c;
+        c2 = fma(c, c, c2);
+      }
+    }
+    *ctl += c1;
+    *ctl2 += c2;
+  }
+}
+
 // Where the per-maturity constants are read from: global memory (any number of maturities), the
 // kernel parameter bank indexed by the maturity (up to kInlineSegs), or -- one maturity, the
 // benchmark shape -- fixed parameter-bank addresses, which the compiler can keep in uniform
@@ -254,7 +292,7 @@ struct ZRing<HEXO_NORMAL_F64> {
 // then reads at most two register pairs.
 enum : int { kSegsGlobal = 0, kSegsInline = 1, kSegsSingle = 2 };
 
-template <int PAYOFF, int NORMAL_MODE, int SEGS, class Gen = Shishua>
+template <int PAYOFF, int NORMAL_MODE, int SEGS, class Gen = Shishua, bool CV = false>
 __global__ void __launch_bounds__(kMaxBlock, kMinBlocksPerSM)
 heston_qe_paths_kernel(const __grid_constant__ PathArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -276,14 +314,19 @@ heston_qe_paths_kernel(const __grid_constant__ PathArgs a) {
   sp += 32 * 8;
   double* fvbuf = reinterpret_cast<double*>(sp) + 32 * warp;
   sp += (size_t)32 * 8 * nwarps;
-  double* acc_all = a.gacc ? a.gacc + (size_t)blockIdx.x * nwarps * a.n_acc
+#define HEXO_N_ACC (CV ? 3 * a.n_opts + 2 * a.n_seg : 2 * a.n_opts)
+  // The plain case spells its offsets out as the 64-bit product chain it has always been: the
+  // register allocation of the whole kernel (114 registers, 1 % faster step loop) hangs on it.
+  double* acc_all = a.gacc ? a.gacc + (CV ? (size_t)blockIdx.x * nwarps * HEXO_N_ACC
+                                         : (size_t)blockIdx.x * nwarps * 2 * a.n_opts)
                            : reinterpret_cast<double*>(sp);
-  double* my_sum = acc_all + (size_t)warp * a.n_acc;  // lane-owned slots
+  double* my_sum =  // lane-owned slots
+      acc_all + (CV ? (size_t)warp * HEXO_N_ACC : (size_t)warp * 2 * a.n_opts);
   double* my_sq = my_sum + a.n_opts;
   double* my_cross = my_sq + a.n_opts;    // cv only: sum pf c per option ...
   double* my_ctl = my_cross + a.n_opts;   // ... and sum c, sum c^2 per maturity (lane 0)
   if (!a.gacc)
-    for (uint32_t j = lane; j < a.n_acc; j += 32) my_sum[j] = 0.0;
+    for (uint32_t j = lane; j < HEXO_N_ACC; j += 32) my_sum[j] = 0.0;
   exp_table_init(exptab, tid, T);
 
   const uint64_t slot = (uint64_t)blockIdx.x * T + tid;
@@ -427,7 +470,7 @@ heston_qe_paths_kernel(const __grid_constant__ PathArgs a) {
       __syncwarp();
       // final_payoff for every strike of this chain (HSimulation.tpp:39-40): lane
       // l owns strikes l, l+32, ... and walks the warp's 32 final values.
-      if (!a.cv) {
+      if (!CV) {
         for (uint32_t j = lane; j < g.n_strikes; j += 32) {
           const double K = __ldg(a.strikes + g.first_opt + j);
           double s = 0.0, q = 0.0;
@@ -443,48 +486,22 @@ heston_qe_paths_kernel(const __grid_constant__ PathArgs a) {
           my_sq[g.first_opt + j] += q;
         }
       } else {
-        // control variate: the same walk also collects sum pf c, c = final value - S
-        for (uint32_t j = lane; j < g.n_strikes; j += 32) {
-          const double K = __ldg(a.strikes + g.first_opt + j);
-          double s = 0.0, q = 0.0, x = 0.0;
-#pragma unroll 8
-          for (int l = 0; l < 32; ++l) {
-            if ((amask >> l) & 1u) {
-              const double f = fvbuf[l];
-              const double pf = fmax(f - K, 0.0);
-              s += pf;
-              q = fma(pf, pf, q);
-              x = fma(pf, f - a.S, x);
-            }
-          }
-          my_sum[g.first_opt + j] += s;
-          my_sq[g.first_opt + j] += q;
-          my_cross[g.first_opt + j] += x;
-        }
-        if (lane == 0) {  // sum c, sum c^2 of this maturity, in lane order
-          double c1 = 0.0, c2 = 0.0;
-          for (int l = 0; l < 32; ++l) {
-            if ((amask >> l) & 1u) {
-              const double c = fvbuf[l] - a.S;
-              c1 += c;
-              c2 = fma(c, c, c2);
-            }
-          }
-          my_ctl[k] += c1;
-          my_ctl[a.n_seg + k] += c2;
-        }
+        accumulate_with_control(fvbuf, amask, lane, a.strikes + g.first_opt, g.n_strikes, a.S,
+                                my_sum + g.first_opt, my_sq + g.first_opt, my_cross + g.first_opt,
+                                my_ctl + k, my_ctl + a.n_seg + k);
       }
     }
   }
 
   // warps -> block partial, fixed order
   __syncthreads();
-  const uint32_t n2 = a.n_acc;
+  const uint32_t n2 = HEXO_N_ACC;
   for (uint32_t j = tid; j < n2; j += T) {
     double s = 0.0;
     for (int w = 0; w < nwarps; ++w) s += acc_all[(size_t)w * n2 + j];
     a.partials[(size_t)blockIdx.x * n2 + j] = s;
   }
+#undef HEXO_N_ACC
 }
 
 }  // namespace hexo
