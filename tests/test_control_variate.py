@@ -150,6 +150,22 @@ def test_gpu_cv_sums_match_oracle(gpu, name, payoff, T, K, steps, n_paths, n_str
 
 
 @pytest.mark.gpu
+def test_gpu_cv_very_wide_chains_use_device_accumulators(gpu):
+    """6000 strikes over two maturities: 3 n_opts + 2 n_chains accumulators per warp do not fit
+    shared memory, the kernel accumulates in device memory.  Same sums as the oracle."""
+    import hestonexotics_b200 as hx
+    K = list(np.linspace(50, 150, 3000))
+    T = [0.25, 0.5]
+    c = oa.Contract(oa.EUROPEAN, T, [K, K], 8)
+    want = c.price_stream_cv(3, 500, 64, normal_mode=oa.NORMAL_F64)
+    r = hx.price_full(hx.HQEAnderson(hx.EuropeanCallNonAdaptive), hx.HParams(*oa.DEFAULT_PARAMS),
+                      100.0, [hx.OptionsChain.from_strikes(t, K) for t in T], 500, 6000, 8, seed=3,
+                      normal_mode="f64", n_streams=64, control_variate="underlying")
+    assert r.sums.size == 3 * 6000 + 4
+    assert np.allclose(r.sums, want, rtol=1e-10, atol=1e-7)
+
+
+@pytest.mark.gpu
 def test_gpu_cv_reduces_the_error_and_keeps_the_price(gpu):
     """cfg1-like Asian chain: same paths, standard errors 1.5-5x smaller in and at the money, prices
     within the plain Monte-Carlo error; also through hexo_gpu_price, price_multi and price_batch."""

@@ -20,5 +20,8 @@ for scheme in (A, E):
                 assert np.isfinite(r.prices).all()
     r = hx.price_full(scheme, p, 100.0, many, 500, None, 6, n_streams=257)   # > 8 segments
     r = hx.price_full(scheme, p, 100.0, wide, 300, None, 4, n_streams=64)    # device accumulators
+    r = hx.price_full(scheme, p, 100.0, many, 500, None, 6, n_streams=257, control_variate="underlying")
+    r = hx.price_full(scheme, p, 100.0, one, 500, None, 6, n_streams=100, control_variate="underlying")
+    r = hx.price_full(scheme, p, 100.0, wide, 300, None, 4, n_streams=64, control_variate="underlying")
 pr, se, ms = hx.price_batch(A, [p, p, p], 100.0, one, 500, None, 10, n_lanes=2)
 print("sanitize probe ok", r.prices[:2], pr[:, 0])
