@@ -26,6 +26,8 @@ struct FmConst {
   double magic;                        // 1.5 * 2^52
   double tiny;                         // 1e-300: keeps sqrt arguments off exact zero
   double u_max;                        // largest double below 1
+  double log_c[9];                     // 1/19, 1/17, ... 1/3: atanh series of fast_log
+  double ln2_hi, ln2_lo;               // ln2 split so that e * ln2_hi is exact
 };
 __constant__ FmConst kFm = {
     1.0 / 40320.0, 1.0 / 5040.0,
@@ -35,6 +37,9 @@ __constant__ FmConst kFm = {
     6755399441055744.0,
     1e-300,
     0.99999999999999988898,
+    {1.0 / 19.0, 1.0 / 17.0, 1.0 / 15.0, 1.0 / 13.0, 1.0 / 11.0, 1.0 / 9.0, 1.0 / 7.0, 1.0 / 5.0,
+     1.0 / 3.0},
+    6.93147180369123816490e-01, 1.90821492927058770002e-10,
 };
 
 __device__ __forceinline__ double mufu_rcp64(double a) {
@@ -102,18 +107,13 @@ __device__ __forceinline__ double fast_log(double y) {
   const double f = __hiloint2double(hi, __double2loint(y));
   const double s = (f - 1.0) * fast_rcp(f + 1.0);
   const double z = s * s;
-  double p = fma(z, 1.0 / 19.0, 1.0 / 17.0);
-  p = fma(p, z, 1.0 / 15.0);
-  p = fma(p, z, 1.0 / 13.0);
-  p = fma(p, z, 1.0 / 11.0);
-  p = fma(p, z, 1.0 / 9.0);
-  p = fma(p, z, 1.0 / 7.0);
-  p = fma(p, z, 1.0 / 5.0);
-  p = fma(p, z, 1.0 / 3.0);
+  double p = fma(z, kFm.log_c[0], kFm.log_c[1]);
+#pragma unroll
+  for (int i = 2; i < 9; ++i) p = fma(p, z, kFm.log_c[i]);
   const double lf = fma(p * z, s + s, s + s);        // 2 s (1 + z/3 + z^2/5 + ...)
   const double ed = (double)e;
   // e ln2 with ln2 split so that e * hi part is exact
-  return fma(ed, 6.93147180369123816490e-01, fma(ed, 1.90821492927058770002e-10, lf));
+  return fma(ed, kFm.ln2_hi, fma(ed, kFm.ln2_lo, lf));
 }
 
 __device__ __forceinline__ void exp_table_init(double* tab, int tid, int nthreads) {
