@@ -305,6 +305,31 @@ def test_cfg4_quirk_bias_is_reproduced(gpu):
     assert a.prices[0] - r.prices[0] > 5 * np.hypot(r.stderr[0], a.stderr[0])
 
 
+def test_cfg4_full_size_in_two_shards(gpu):
+    """BASELINE config 4 at its full size (10^9 paths x 1024 steps), run as two shards of the
+    stream range (1/4 + 3/4) whose sums are added -- what two ranks would do.  Size-independent
+    properties: (a) with strike 0 the payoff is the average itself, whose expectation on the
+    reference's grid is S (1 - 1/steps) (1024 steps land on T, so the last trapezoid is replaced
+    by X_N - X_{N-1}, mean zero; SURVEY finding 6); (b) the ATM price sits in the band the
+    reference's own CPU code gives for this configuration; (c) a shard is bit-reproducible."""
+    n, steps = 1_000_000_000, 1024
+    rq = hx.pricing._Request(ASIAN, P0, 100.0, chains_of([1.0], [[0.0, 100.0]]), n, 2, steps, 1,
+                             "f32", 0)
+    rq.req.n_streams = gpu.hexo_gpu_default_streams(n, 2, 1)
+    ns = int(rq.req.n_streams)
+    cut = ns // 4
+    parts = []
+    for begin, count in ((0, cut), (cut, ns - cut), (0, cut)):
+        sums = np.zeros(4)
+        _lib.check(gpu.hexo_gpu_price_shard(C.byref(rq.req), begin, count,
+                                            sums.ctypes.data_as(_lib.c_double_p), None))
+        parts.append(sums)
+    assert np.array_equal(parts[0], parts[2])                                   # (c)
+    prices, se = hx.pricing._finish(rq, parts[0] + parts[1])
+    assert abs(prices[0] - 100.0 * (1.0 - 1.0 / steps)) < 5 * se[0] + 0.01      # (a) + QE drift bias
+    assert 4.215 < prices[1] < 4.232 and se[1] < 2e-4                           # (b)
+
+
 def test_cfg3_chain_monotone_and_consistent(gpu):
     """cfg3 shape: 64 strikes x 8 maturities in one call; call prices fall with the strike and
     the 8-chain call agrees with a single-chain call of the first maturity within MC error."""
