@@ -18,9 +18,10 @@ LIB_PATH = os.path.join(LIB_DIR, "libhexo_gpu.so")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-shared",
+    "-Xcompiler", "-fPIC",
     "-Xptxas", "-v",
 ]
+OBJ_DIR = os.path.join(LIB_DIR, "obj")
 
 
 def _sources():
@@ -41,23 +42,40 @@ def needs_build() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile every .cu under csrc/ into one shared library.  Returns its path."""
+    """Compile every .cu under csrc/ (one nvcc per file, in parallel) and link them into one
+    shared library.  Returns its path."""
     if not force and not needs_build():
         return LIB_PATH
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found: cannot build libhexo_gpu.so")
-    os.makedirs(LIB_DIR, exist_ok=True)
-    tmp = LIB_PATH + ".tmp"
-    cmd = [nvcc, *NVCC_FLAGS, "-o", tmp, *_sources()]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if verbose or res.returncode != 0:
-        sys.stderr.write(res.stdout + res.stderr)
-    if res.returncode != 0:
-        raise RuntimeError("nvcc failed building libhexo_gpu.so (see stderr)")
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    srcs = _sources()
+    objs = [os.path.join(OBJ_DIR, os.path.basename(s)[:-3] + ".o") for s in srcs]
+
+    def compile_one(pair):
+        src, obj = pair
+        return subprocess.run([nvcc, *NVCC_FLAGS, "-c", "-o", obj, src], capture_output=True,
+                              text=True)
+
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=min(len(srcs), os.cpu_count() or 1)) as pool:
+        results = list(pool.map(compile_one, zip(srcs, objs)))
+    log = "".join(r.stdout + r.stderr for r in results)
+    failed = [s for s, r in zip(srcs, results) if r.returncode != 0]
+    if not failed:
+        tmp = LIB_PATH + ".tmp"
+        link = subprocess.run([nvcc, "-shared", "-o", tmp, *objs], capture_output=True, text=True)
+        log += link.stdout + link.stderr
+        if link.returncode != 0:
+            failed = ["link"]
+    if verbose or failed:
+        sys.stderr.write(log)
+    if failed:
+        raise RuntimeError(f"nvcc failed building libhexo_gpu.so ({failed}; see stderr)")
     os.replace(tmp, LIB_PATH)
     with open(os.path.join(LIB_DIR, "ptxas.log"), "w") as f:
-        f.write(res.stdout + res.stderr)
+        f.write(log)
     return LIB_PATH
 
 

@@ -29,7 +29,8 @@ struct FmConst {
   double log_c[9];                     // 1/19, 1/17, ... 1/3: atanh series of fast_log
   double ln2_hi, ln2_lo;               // ln2 split so that e * ln2_hi is exact
 };
-__constant__ FmConst kFm = {
+// static: one copy per translation unit (the kernels are built in several)
+static __constant__ FmConst kFm = {
     1.0 / 40320.0, 1.0 / 5040.0,
     1.0 / 720.0, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0,
     46.166241308446828384,

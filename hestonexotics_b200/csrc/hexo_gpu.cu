@@ -32,9 +32,7 @@
 #include <vector>
 
 #include "../../include/hexo_gpu.h"
-#include "path_kernel.cuh"
-#include "path_kernel_il.cuh"
-#include "path_kernel_ws.cuh"
+#include "path_kernels.h"
 
 namespace hexo {
 
@@ -431,58 +429,22 @@ struct Plan {
   bool il = false;  // interleaved look-ahead kernel (path_kernel_il.cuh)
 };
 
-typedef void (*PathKernel)(const PathArgs);
-template <int SEGS, class Gen, bool CV>
-static PathKernel pick_kernel_t(int payoff, int normal_mode) {
-  if (payoff == HEXO_PAYOFF_ASIAN)
-    return normal_mode == HEXO_NORMAL_F64
-               ? heston_qe_paths_kernel<HEXO_PAYOFF_ASIAN, 1, SEGS, Gen, CV>
-               : heston_qe_paths_kernel<HEXO_PAYOFF_ASIAN, 0, SEGS, Gen, CV>;
-  return normal_mode == HEXO_NORMAL_F64
-             ? heston_qe_paths_kernel<HEXO_PAYOFF_EUROPEAN, 1, SEGS, Gen, CV>
-             : heston_qe_paths_kernel<HEXO_PAYOFF_EUROPEAN, 0, SEGS, Gen, CV>;
-}
-template <class Gen, bool CV>
-static PathKernel pick_kernel_g(int payoff, int normal_mode, uint32_t n_seg) {
-  return n_seg == 1 ? pick_kernel_t<kSegsSingle, Gen, CV>(payoff, normal_mode)
-         : n_seg <= (uint32_t)kInlineSegs
-             ? pick_kernel_t<kSegsInline, Gen, CV>(payoff, normal_mode)
-             : pick_kernel_t<kSegsGlobal, Gen, CV>(payoff, normal_mode);
-}
-// Philox and the control variate: only the default kernel shape carries them (not WS / IL)
+// The path-kernel instantiations live in their own translation units (path_kernels_*.cu), which
+// build in parallel; path_kernels.h declares the selectors.
 static PathKernel pick_kernel(int payoff, int normal_mode, uint32_t n_seg, int rng_mode = 0,
                               bool cv = false) {
-  if (rng_mode == HEXO_RNG_PHILOX)
-    return cv ? pick_kernel_g<PhiloxGen, true>(payoff, normal_mode, n_seg)
-              : pick_kernel_g<PhiloxGen, false>(payoff, normal_mode, n_seg);
-  return cv ? pick_kernel_g<Shishua, true>(payoff, normal_mode, n_seg)
-            : pick_kernel_g<Shishua, false>(payoff, normal_mode, n_seg);
-}
-
-typedef void (*PathKernelWs)(const PathArgs, const uint32_t);
-template <bool INL>
-static PathKernelWs pick_ws_kernel_t(int payoff, int normal_mode) {
-  if (payoff == HEXO_PAYOFF_ASIAN)
-    return normal_mode == HEXO_NORMAL_F64 ? heston_qe_paths_ws_kernel<HEXO_PAYOFF_ASIAN, 1, INL>
-                                          : heston_qe_paths_ws_kernel<HEXO_PAYOFF_ASIAN, 0, INL>;
-  return normal_mode == HEXO_NORMAL_F64 ? heston_qe_paths_ws_kernel<HEXO_PAYOFF_EUROPEAN, 1, INL>
-                                        : heston_qe_paths_ws_kernel<HEXO_PAYOFF_EUROPEAN, 0, INL>;
+  const int segs = n_seg == 1                       ? kSegsSingle
+                   : n_seg <= (uint32_t)kInlineSegs ? kSegsInline
+                                                    : kSegsGlobal;
+  if (rng_mode == HEXO_RNG_PHILOX) return path_kernel_philox(payoff, normal_mode, segs, cv);
+  return cv ? path_kernel_shishua_cv(payoff, normal_mode, segs)
+            : path_kernel_shishua(payoff, normal_mode, segs);
 }
 static PathKernelWs pick_ws_kernel(int payoff, int normal_mode, uint32_t n_seg) {
-  return n_seg <= (uint32_t)kInlineSegs ? pick_ws_kernel_t<true>(payoff, normal_mode)
-                                        : pick_ws_kernel_t<false>(payoff, normal_mode);
-}
-template <bool INL>
-static PathKernel pick_il_kernel_t(int payoff, int normal_mode) {
-  if (payoff == HEXO_PAYOFF_ASIAN)
-    return normal_mode == HEXO_NORMAL_F64 ? heston_qe_paths_il_kernel<HEXO_PAYOFF_ASIAN, 1, INL>
-                                          : heston_qe_paths_il_kernel<HEXO_PAYOFF_ASIAN, 0, INL>;
-  return normal_mode == HEXO_NORMAL_F64 ? heston_qe_paths_il_kernel<HEXO_PAYOFF_EUROPEAN, 1, INL>
-                                        : heston_qe_paths_il_kernel<HEXO_PAYOFF_EUROPEAN, 0, INL>;
+  return path_kernel_ws(payoff, normal_mode, n_seg <= (uint32_t)kInlineSegs);
 }
 static PathKernel pick_il_kernel(int payoff, int normal_mode, uint32_t n_seg) {
-  return n_seg <= (uint32_t)kInlineSegs ? pick_il_kernel_t<true>(payoff, normal_mode)
-                                        : pick_il_kernel_t<false>(payoff, normal_mode);
+  return path_kernel_il(payoff, normal_mode, n_seg <= (uint32_t)kInlineSegs);
 }
 static bool use_il() {
   const char* e = getenv("HEXO_IL");

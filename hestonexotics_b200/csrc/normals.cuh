@@ -83,7 +83,7 @@ __device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
 
 // far tail of as241.f90:110-114 (r > 5, i.e. p < 1.4e-11) and the p in {0,1} case
 // (:99-103): rare, evaluated in plain scalar code
-__device__ __noinline__ float ppnd_far_tail_f32(float q, float t) {
+static __device__ __noinline__ float ppnd_far_tail_f32(float q, float t) {
   using P = Ppnd;
   if (!(t < 3.0e38f)) return 0.0f;  // v == 0: the reference returns 0 with IFAULT = 1
   const float r = sqrtf(t) - (float)P::SPLIT2;
@@ -144,7 +144,7 @@ __device__ __forceinline__ float normal_tail_mid_f32(uint64_t w, float& t) {
 }
 
 // the far tail for the same draw (rare)
-__device__ __noinline__ float normal_tail_far_f32(uint64_t w, float t) {
+static __device__ __noinline__ float normal_tail_far_f32(uint64_t w, float t) {
   const uint32_t hi = (uint32_t)(w >> 32);
   return ppnd_far_tail_f32((hi & 0x80000000u) ? 1.0f : -1.0f, t);
 }
@@ -177,7 +177,7 @@ __device__ __forceinline__ double normal_tail_mid_f64(uint64_t w, double& rr) {
 }
 
 // far tail (:110-114) and p in {0,1} (:99-103) for the same draw (rare)
-__device__ __noinline__ double normal_tail_far_f64(uint64_t w, double rr) {
+static __device__ __noinline__ double normal_tail_far_f64(uint64_t w, double rr) {
   using P = Ppnd;
   const double p = u64_to_unit(w);
   const double q = p - 0.5;
