@@ -37,6 +37,13 @@ constexpr int kMaxBlock = 256;
 #endif
 constexpr int kMinBlocksPerSM = HEXO_MIN_BLOCKS;  // register budget: 65536 / (256 * this)
 constexpr int kStepsPerRound = 8;  // one shishua round = 16 words = 8 steps
+// Steps the default kernel transforms per refill.  F32 normals: two generator rounds -- the
+// per-lane tail loop then runs max-over-lanes(ceil(tails/2)) iterations for 32 draws instead of
+// twice that maximum for 16, and the refill overhead is paid half as often.  F64 normals keep one
+// round: their ring is twice as wide and two blocks per SM would not fit.
+__host__ __device__ constexpr int ring_steps(int normal_mode) {
+  return normal_mode == HEXO_NORMAL_F64 ? kStepsPerRound : 2 * kStepsPerRound;
+}
 constexpr int kInlineSegs = 8;     // maturities whose constants travel as kernel parameters
 
 struct PathArgs {
@@ -75,8 +82,9 @@ struct PathArgs {
 __host__ __device__ inline size_t path_kernel_smem(int block, uint32_t n_acc, int normal_mode,
                                                    bool acc_in_smem = true) {
   const int warps = block / 32;
-  const size_t zbytes = (normal_mode == HEXO_NORMAL_F64 ? 16 : 8) * (size_t)kStepsPerRound * block;
-  return zbytes + (size_t)16 * kStepsPerRound * block + 32 * 8 + (size_t)32 * 8 * warps +
+  const size_t steps = ring_steps(normal_mode);
+  const size_t zbytes = (normal_mode == HEXO_NORMAL_F64 ? 16 : 8) * steps * block;
+  return zbytes + (size_t)16 * steps * block + 32 * 8 + (size_t)32 * 8 * warps +
          (acc_in_smem ? (size_t)warps * n_acc * 8 : 0);
 }
 
@@ -152,6 +160,22 @@ struct ZRing<HEXO_NORMAL_F32> {
     }
     tail_phase(tails, wcol, wstride, zcol, zstride);
   }
+  // central phase of one generator round (8 steps) whose first step lives at zcol0; returns the
+  // 16 tail bits of the round
+  static __device__ __forceinline__ uint32_t central_round(const uint64_t (&o)[16], uint32_t zcol0,
+                                                           uint32_t zstride) {
+    uint32_t tails = 0;
+#pragma unroll
+    for (int s = 0; s < kStepsPerRound; ++s) {
+      float zv, zx;
+      bool t0, t1;
+      normal2_central_f32(o[2 * s], o[2 * s + 1], zv, zx, t0, t1);
+      sts_b64(zcol0 + s * zstride, pack2(zv, zx));
+      if (t0) tails |= 1u << (2 * s);
+      if (t1) tails |= 2u << (2 * s);
+    }
+    return tails;
+  }
   // one (central normals, tail flag) pair of a step, for kernels that spread the central phase
   // over the step loop: returns the two tail bits
   static __device__ __forceinline__ uint32_t central_step(uint32_t waddr, uint32_t zaddr) {
@@ -210,6 +234,20 @@ struct ZRing<HEXO_NORMAL_F64> {
       if (t1) tails |= 2u << (2 * s);
     }
     tail_phase(tails, wcol, wstride, zcol, zstride);
+  }
+  static __device__ __forceinline__ uint32_t central_round(const uint64_t (&o)[16], uint32_t zcol0,
+                                                           uint32_t zstride) {
+    uint32_t tails = 0;
+#pragma unroll
+    for (int s = 0; s < kStepsPerRound; ++s) {
+      bool t0, t1;
+      const double zv = normal_central_f64(o[2 * s], t0);
+      const double zx = normal_central_f64(o[2 * s + 1], t1);
+      sts_f64x2(zcol0 + s * zstride, zv, zx);
+      if (t0) tails |= 1u << (2 * s);
+      if (t1) tails |= 2u << (2 * s);
+    }
+    return tails;
   }
   static __device__ __forceinline__ uint32_t central_step(uint32_t waddr, uint32_t zaddr) {
     uint64_t w0, w1;
@@ -300,15 +338,16 @@ heston_qe_paths_kernel(const __grid_constant__ PathArgs a) {
   const int T = blockDim.x, nwarps = T >> 5;
   using Ring = ZRing<NORMAL_MODE>;
   constexpr bool kAsian = PAYOFF == HEXO_PAYOFF_ASIAN;
+  constexpr int kRing = ring_steps(NORMAL_MODE);  // steps per refill
 
   unsigned char* sp = smem_raw;
   // pin32: keep the ring addresses in registers; otherwise ptxas re-derives them from
   // %tid / %ntid / the shared window base inside the step and tail loops (~20 instructions)
   const uint32_t zstride = pin32(Ring::kBytesPerStep * T), ustride = pin32(16 * T);
   const uint32_t ucol = pin32(smem_addr(sp) + 16 * tid);  // raw (variance, spot) words per step
-  sp += (size_t)16 * kStepsPerRound * T;
+  sp += (size_t)16 * kRing * T;
   const uint32_t zcol = pin32(smem_addr(sp) + Ring::kBytesPerStep * tid);
-  sp += (size_t)Ring::kBytesPerStep * kStepsPerRound * T;
+  sp += (size_t)Ring::kBytesPerStep * kRing * T;
   double* exptab = reinterpret_cast<double*>(sp);
   const uint32_t exptab_s = pin32(smem_addr(sp));
   sp += 32 * 8;
@@ -345,18 +384,31 @@ heston_qe_paths_kernel(const __grid_constant__ PathArgs a) {
           : 0u;
 
   Gen rng;  // Shishua (the reference's generator) or PhiloxGen (optional counter mode)
-  auto refill = [&](uint64_t (&o)[16]) {
+  // one generator round -> raw words and central normals of steps [8 r, 8 r + 8) of the ring;
+  // returns the round's 16 tail bits
+  auto park_round = [&](const uint64_t (&o)[16], int r) -> uint32_t {
+    const uint32_t u0 = ucol + r * kStepsPerRound * ustride;
 #pragma unroll
     for (int s = 0; s < kStepsPerRound; ++s) {  // two 64-bit stores: a 128-bit store would need
-      sts_b64(ucol + s * ustride, o[2 * s]);      // the four words moved into an aligned quad
-      sts_b64(ucol + s * ustride + 8, o[2 * s + 1]);
+      sts_b64(u0 + s * ustride, o[2 * s]);        // the four words moved into an aligned quad
+      sts_b64(u0 + s * ustride + 8, o[2 * s + 1]);
     }
-    Ring::fill(o, ucol, ustride, zcol, zstride);
+    return Ring::central_round(o, zcol + r * kStepsPerRound * zstride, zstride);
+  };
+  // refill the whole ring: kRing / 8 generator rounds, then ONE tail phase over all their draws
+  auto refill = [&](uint64_t (&o)[16], bool have_first) {
+    uint32_t tails = 0;
+#pragma unroll
+    for (int r = 0; r < kRing / kStepsPerRound; ++r) {
+      if (r > 0 || !have_first) rng.round(o);
+      tails |= park_round(o, r) << (16 * r);
+    }
+    Ring::tail_phase(tails, ucol, ustride, zcol, zstride);
   };
   {
     uint64_t o[16];
     rng.init(a.seed, sid, 0, 0, o);
-    refill(o);
+    refill(o, true);
   }
   uint32_t pos = 0;  // next unread step of the round
   __syncthreads();   // exptab
@@ -411,15 +463,14 @@ heston_qe_paths_kernel(const __grid_constant__ PathArgs a) {
           double Vold = V, zx_pend = 0.0;  // (V_{j-1}, Z_X of step j-1) of the pending half
           bool first = true;
           while (count) {
-            if (pos == kStepsPerRound) {
+            if (pos == kRing) {
               if (!a.dev_no_refill) {
                 uint64_t o[16];
-                rng.round(o);
-                refill(o);
+                refill(o, false);
               }
               pos = 0;
             }
-            uint32_t m = min(kStepsPerRound - pos, count);
+            uint32_t m = min(kRing - pos, count);
             count -= m;
             uint32_t za = zcol + pos * zstride, ua = ucol + pos * ustride;
             pos += m;
