@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libhexo_gpu.so")
+# HEXO_GPU_LIB: another build of the same CUDA library (A/B comparisons of kernel variants)
+LIB_PATH = os.environ.get("HEXO_GPU_LIB") or os.path.join(HERE, "lib", "libhexo_gpu.so")
 
 # names of every function include/hexo_gpu.h declares (checked by tests)
 ABI_SYMBOLS = (

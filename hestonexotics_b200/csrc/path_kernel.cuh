@@ -488,10 +488,33 @@ heston_qe_paths_kernel(const __grid_constant__ PathArgs a) {
             for (; m; --m, za += zstride, ua += ustride) {
               double zv, zx;
               Ring::get(za, zv, zx);
-              // second half of the previous step
-              spot_half(Vold, V, zx_pend, with_x, !kAsian);
-              // first half of this step
-              const double Vn = qe_variance(g, V, zv, [ua]() { return u64_to_unit(lds_b64(ua)); });
+              // Second half of the previous step and first half of this one, straight-line
+              // parts first: two independent dependency chains in ONE basic block.  The rare
+              // cases of both (|log-return| > 0.08; psi >= 1.5) share a single branch behind
+              // them -- a branch per half would put a convergence barrier between the chains
+              // and ptxas then runs them one after the other.
+              const double delta = qe_logreturn(g, Vold, V, zx_pend);
+              QeVarMid mid;
+              double Vn = qe_variance_quad(g, V, zv, mid);
+              if (kAsian) {
+                double Xn = grow_spot_poly(X, delta);
+                const bool rare_x = grow_spot_is_rare(delta);
+                if (rare_x | mid.rare) {
+                  if (rare_x) Xn = grow_spot_rare(X, delta, exptab_s);
+                  if (mid.rare)
+                    Vn = qe_variance_rare(mid, [ua]() { return u64_to_unit(lds_b64(ua)); });
+                }
+                X = Xn;
+                sumX += X;
+              } else {
+                lnX += delta;
+                if (decltype(with_x)::value) {
+                  Xprev = X;
+                  X = fast_exp(lnX, exptab_s);
+                }
+                if (mid.rare)
+                  Vn = qe_variance_rare(mid, [ua]() { return u64_to_unit(lds_b64(ua)); });
+              }
               Vold = V;
               V = Vn;
               zx_pend = zx;

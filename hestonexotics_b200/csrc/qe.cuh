@@ -47,35 +47,63 @@ struct SegConst {
 // the log-spot / exp half of step i hangs off (V_i, V_{i+1}) and can overlap the
 // variance half of step i+1.
 
+// The variance half (src/HSimulation.tpp:59-73) comes in two pieces so that the path kernel can keep the straight-line
+// part of BOTH halves of its pipelined iteration in one basic block and send the rare cases of
+// either half through one shared branch (a convergence barrier in the middle of the block
+// stops ptxas from interleaving the two dependency chains).
+struct QeVarMid {
+  double m, s2h;  // :59, :60 (s^2/2)
+  bool rare;      // psi >= 1.5: the quadratic value has to be replaced by qe_variance_rare
+};
+
+// quadratic branch, evaluated unconditionally (NaN when psi > 2; replaced where mid.rare)
+__device__ __forceinline__ double qe_variance_quad(const SegConst& g, const double V,
+                                                   const double zv, QeVarMid& mid) {
+  const double m = fma(V, g.D, g.m0);                       // :59
+  const double s2h = fabs(fma(V, g.c1h, g.c2h));            // :60  (s^2/2)
+  const double w = fma(m, m, -s2h);                         // m^2 (1 - psi/2)
+  const double sw = fast_sqrt(w);                           // a b^2
+  const double dm = m - sw;                                 // a
+  const double me = fast_sqrt(fma(sw, dm, kFm.tiny));       // a b; sw dm >= 0, kept off exact 0
+  mid.m = m;
+  mid.s2h = s2h;
+  mid.rare = !(3.0 * w > s2h);                              // :63  psi >= 1.5
+  return fma(zv, fma(dm, zv, me + me), sw);                 // :64-68
+}
+
+// Exponential / zero-mass branch (:70-73), a few per cent of the warp-steps, straight-line
+// code as well.  With q = m^2 (psi + 1) = m^2 + s^2:
+//   p = (psi-1)/(psi+1),  p < U  <=>  s^2 - m^2 < U q
+//   beta = 2/(m (psi+1)) = 2 m / q,  1 - p = 2 m^2 / q
+//   V' = ln((1-p)/(1-U)) / beta = q/(2m) ln(2 m^2 / (q (1-U)))
+//   uv : callable returning the variance UNIFORM of the same draw
+template <class UniformFn>
+__device__ __forceinline__ double qe_variance_rare(const QeVarMid& mid, const UniformFn& uv) {
+  const double m = mid.m;
+  const double m2 = m * m, s2 = mid.s2h + mid.s2h;
+  const double q = m2 + s2;
+  // U = 1.0 (probability 2^-54) would make the reference take log(x/0) = inf;
+  // clamp to the largest double below 1 instead.
+  const double u = fmin(uv(), kFm.u_max);                   // :72
+  double v = 0.0;
+  // p >= 0.2 here, and a warp rarely has more than one lane on this path: testing U against p
+  // first skips the logarithm (the longest dependency chain of the kernel) about as often
+  if (s2 - m2 < u * q) {                                    // :73  p < U
+    const double y = (m2 + m2) * fast_rcp(q * (1.0 - u));
+    v = 0.5 * q * fast_rcp(m) * fast_log(y);
+  }
+  return v;
+}
+
 // Variance half, src/HSimulation.tpp:59-73.
 //   zv : variance normal (used when psi < 1.5)
 //   uv : callable returning the variance UNIFORM of the same draw (psi >= 1.5)
 template <class UniformFn>
 __device__ __forceinline__ double qe_variance(const SegConst& g, const double V, const double zv,
                                               const UniformFn& uv) {
-  const double m = fma(V, g.D, g.m0);                       // :59
-  const double s2h = fabs(fma(V, g.c1h, g.c2h));            // :60  (s^2/2)
-  const double w = fma(m, m, -s2h);                         // m^2 (1 - psi/2)
-  // quadratic branch, evaluated unconditionally (NaN when psi > 2, replaced below)
-  const double sw = fast_sqrt(w);                           // a b^2
-  const double dm = m - sw;                                 // a
-  const double me = fast_sqrt(fma(sw, dm, kFm.tiny));       // a b; sw dm >= 0, kept off exact 0
-  double Vn = fma(zv, fma(dm, zv, me + me), sw);            // :64-68
-  if (!(3.0 * w > s2h)) {                                   // :63  psi >= 1.5
-    // Exponential / zero-mass branch (:70-73), a few per cent of the warp-steps, so it is
-    // straight-line code as well.  With q = m^2 (psi + 1) = m^2 + s^2:
-    //   p = (psi-1)/(psi+1),  p < U  <=>  s^2 - m^2 < U q
-    //   beta = 2/(m (psi+1)) = 2 m / q,  1 - p = 2 m^2 / q
-    //   V' = ln((1-p)/(1-U)) / beta = q/(2m) ln(2 m^2 / (q (1-U)))
-    const double m2 = m * m, s2 = s2h + s2h;
-    const double q = m2 + s2;
-    // U = 1.0 (probability 2^-54) would make the reference take log(x/0) = inf;
-    // clamp to the largest double below 1 instead.
-    const double u = fmin(uv(), kFm.u_max);                 // :72
-    const double y = (m2 + m2) * fast_rcp(q * (1.0 - u));
-    const double v = 0.5 * q * fast_rcp(m) * fast_log(y);
-    Vn = (s2 - m2 < u * q) ? v : 0.0;                       // :73
-  }
+  QeVarMid mid;
+  double Vn = qe_variance_quad(g, V, zv, mid);
+  if (mid.rare) Vn = qe_variance_rare(mid, uv);
   return Vn;
 }
 
@@ -93,8 +121,7 @@ __device__ __forceinline__ double qe_logreturn(const SegConst& g, const double V
 // small, so e^delta - 1 is a degree-8 Taylor polynomial for |delta| <= 0.08 (remainder
 // < 4e-16) -- no range reduction, no table look-up -- and the table-based fast_exp
 // otherwise (rare: 6 standard deviations of a daily step at 20 % volatility).
-__device__ __forceinline__ double grow_spot(const double X, const double delta,
-                                            const uint32_t exptab_saddr) {
+__device__ __forceinline__ double grow_spot_poly(const double X, const double delta) {
   double p = fma(delta, kFm.inv40320, kFm.inv5040);
   p = fma(p, delta, kFm.inv720);
   p = fma(p, delta, kFm.inv120);
@@ -102,8 +129,17 @@ __device__ __forceinline__ double grow_spot(const double X, const double delta,
   p = fma(p, delta, kFm.inv6);
   p = fma(p, delta, 0.5);
   p = fma(p, delta, 1.0);
-  double Xn = fma(X, p * delta, X);
-  if (fabs(delta) > 0.08) Xn = X * fast_exp(delta, exptab_saddr);
+  return fma(X, p * delta, X);
+}
+__device__ __forceinline__ bool grow_spot_is_rare(const double delta) { return fabs(delta) > 0.08; }
+__device__ __forceinline__ double grow_spot_rare(const double X, const double delta,
+                                                 const uint32_t exptab_saddr) {
+  return X * fast_exp(delta, exptab_saddr);
+}
+__device__ __forceinline__ double grow_spot(const double X, const double delta,
+                                            const uint32_t exptab_saddr) {
+  double Xn = grow_spot_poly(X, delta);
+  if (grow_spot_is_rare(delta)) Xn = grow_spot_rare(X, delta, exptab_saddr);
   return Xn;
 }
 

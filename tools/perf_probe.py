@@ -1,0 +1,31 @@
+"""Throughput of the path kernel on the BASELINE shapes (development probe, not the bench contract).
+usage: perf_probe.py [scale]   HEXO_GPU_LIB=<variant .so> selects the library under test."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import hestonexotics_b200 as hx
+from hestonexotics_b200 import _lib
+
+lib = _lib.load()
+_lib.check(lib.hexo_gpu_init(0))
+p = hx.HParams(0.04, 0.04, -0.7, 2.0, 0.5)
+stiff = hx.HParams(0.04, 0.04, -0.95, 20.0, 1.0)
+A = hx.HQEAnderson(hx.AAsianCallNonAdaptive); E = hx.HQEAnderson(hx.EuropeanCallNonAdaptive)
+scale = float(sys.argv[1]) if len(sys.argv) > 1 else 1.0
+def run(name, scheme, T, K, n, steps, mode, p=p, rng="shishua", reps=3):
+    ch = [hx.OptionsChain.from_strikes(t, k) for t, k in zip(T, K)]
+    best = None
+    for i in range(reps):
+        r = hx.price_full(scheme, p, 100.0, ch, n, None, steps, seed=1 + i, normal_mode=mode, rng=rng)
+        if i and (best is None or r.kernel_ms < best.kernel_ms): best = r
+    r = best
+    print(f"{name:24s} {mode} {rng:7s} n={n:.0e} steps={steps:4d} ms={r.kernel_ms:8.2f} "
+          f"rate={r.path_steps/r.kernel_ms/1e6:7.2f} G/s price0={r.prices[0]:.4f}+-{r.stderr[0]:.4f}", flush=True)
+print("lib:", _lib.LIB_PATH)
+run("cfg4 asian 1024", A, [1.0], [[100.0]], int(2e7*scale), 1024, "f32")
+run("cfg2 euro 252", E, [1.0], [[100.0]], int(4e6*scale), 252, "f32")
+run("cfg1-shape asian 252", A, [1.0], [[100.0]], int(4e6*scale), 252, "f32")
+run("cfg5 stiff 2520", A, [10.0], [list(np.linspace(70,130,64))], int(2e6*scale), 2520, "f32", stiff)
+run("cfg3 chain 64x8", A, [0.25*k for k in range(1,9)], [list(np.linspace(70,130,64))]*8, int(2e6*scale), 252, "f32")
+run("cfg4 asian 1024", A, [1.0], [[100.0]], int(2e7*scale), 1024, "f64")
+run("cfg4 asian 1024", A, [1.0], [[100.0]], int(2e7*scale), 1024, "f32", rng="philox")
