@@ -140,7 +140,11 @@ __device__ __forceinline__ float normal_tail_mid_f32(uint64_t w, float& t) {
       mufu_rcp(horner8<float>(r, (float)P::D7, (float)P::D6, (float)P::D5, (float)P::D4,
                               (float)P::D3, (float)P::D2, (float)P::D1, 1.0f));
   // sign of q = p - 1/2: negative when the top bit of the draw is clear (as241.f90:116)
-  return __uint_as_float(__float_as_uint(z) ^ (~hi & 0x80000000u));
+  // as ONE lop3 (z ^ (~hi & 0x80000000), truth table 0xD2); left to the compiler this becomes a
+  // lop3 plus a negating add
+  uint32_t zs;
+  asm("lop3.b32 %0, %1, %2, 0x80000000, 0xD2;" : "=r"(zs) : "r"(__float_as_uint(z)), "r"(hi));
+  return __uint_as_float(zs);
 }
 
 // the far tail for the same draw (rare)

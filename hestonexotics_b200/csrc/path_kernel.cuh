@@ -71,8 +71,8 @@ struct PathArgs {
 };
 
 // Shared memory of the path kernel (per block), T = threads, W = warps:
-//   wring  [8][T] the 16 raw words of the current generator round, one (variance
-//                 word, spot word) pair per step.  Kept because the tail phase of
+//   wring  [2][R][T] the raw words of the R steps a refill covers (R = ring_steps), variance
+//                 words first, then spot words.  Kept because the tail phase of
 //                 the normal transform re-reads them and because the psi >= 1.5
 //                 branch needs the UNIFORM of the variance draw (HSimulation.tpp:72)
 //   zring  [8][T] pairs (Z_V, Z_X) of the round, float2 (F32 mode) / double2 (F64)
@@ -136,6 +136,13 @@ __device__ __forceinline__ uint32_t pin32(uint32_t x) {
   return x;
 }
 
+// index of the highest set bit (x != 0): one FLO
+__device__ __forceinline__ uint32_t bfind32(uint32_t x) {
+  uint32_t r;
+  asm("bfind.u32 %0, %1;" : "=r"(r) : "r"(x));
+  return r;
+}
+
 // Raw words -> normals for one generator round, in two phases (normals.cuh):
 // central formula for all 16 draws, then a per-lane loop over this lane's tail draws.
 //   wcol / zcol : shared addresses of this thread's step-0 slots, wstride / zstride
@@ -191,15 +198,15 @@ struct ZRing<HEXO_NORMAL_F32> {
   // MUFU (lg2, sqrt, rcp) latencies of this otherwise serial loop
   static __device__ __forceinline__ void tail_phase(uint32_t tails, uint32_t wcol,
                                                     uint32_t wstride, uint32_t zcol,
-                                                    uint32_t zstride) {
+                                                    uint32_t zstride, uint32_t wplane = 8) {
     while (tails) {
       const int j0 = __ffs(tails) - 1;
       tails &= tails - 1;
       const bool two = tails != 0;
       const int j1 = two ? __ffs(tails) - 1 : j0;
       tails &= tails - 1;
-      const uint64_t w0 = lds_b64(wcol + (j0 >> 1) * wstride + (j0 & 1) * 8);
-      const uint64_t w1 = lds_b64(wcol + (j1 >> 1) * wstride + (j1 & 1) * 8);
+      const uint64_t w0 = lds_b64(wcol + (j0 >> 1) * wstride + (j0 & 1) * wplane);
+      const uint64_t w1 = lds_b64(wcol + (j1 >> 1) * wstride + (j1 & 1) * wplane);
       float t0, t1;
       float z0 = normal_tail_mid_f32(w0, t0), z1 = normal_tail_mid_f32(w1, t1);
       if (fmaxf(t0, t1) > 25.0f) {  // far tail: essentially never
@@ -208,6 +215,50 @@ struct ZRing<HEXO_NORMAL_F32> {
       }
       sts_f32(zcol + (j0 >> 1) * zstride + (j0 & 1) * 4, z0);
       if (two) sts_f32(zcol + (j1 >> 1) * zstride + (j1 & 1) * 4, z1);
+    }
+  }
+  // ---- planar ring of the default kernel (RING steps per refill, a power of two) ------------
+  // Raw words live in two planes [variance words | spot words] of RING steps each, so word j of
+  // the refill (j = RING d + step, d = 0 variance / 1 spot) sits at wcol + j wstride; tail bit j
+  // marks that word.
+  template <int RING>
+  static __device__ __forceinline__ uint32_t central_round_planar(const uint64_t (&o)[16],
+                                                                  int step0, uint32_t zcol,
+                                                                  uint32_t zstride) {
+    static_assert(2 * RING <= 32 && (RING & (RING - 1)) == 0, "tail mask is 32 bits");
+    uint32_t tails = 0;
+#pragma unroll
+    for (int s = 0; s < kStepsPerRound; ++s) {
+      float zv, zx;
+      bool t0, t1;
+      normal2_central_f32(o[2 * s], o[2 * s + 1], zv, zx, t0, t1);
+      sts_b64(zcol + (step0 + s) * zstride, pack2(zv, zx));
+      if (t0) tails |= 1u << (step0 + s);
+      if (t1) tails |= 1u << (RING + step0 + s);
+    }
+    return tails;
+  }
+  template <int RING>
+  static __device__ __forceinline__ void tail_phase_planar(uint32_t tails, uint32_t wcol,
+                                                           uint32_t wstride, uint32_t zcol,
+                                                           uint32_t zstride) {
+    constexpr int kLog = RING == 16 ? 4 : RING == 8 ? 3 : RING == 4 ? 2 : 1;
+    while (tails) {  // two tail draws per iteration (independent evaluations hide MUFU latency)
+      const uint32_t j0 = bfind32(tails);
+      const uint32_t b0 = 1u << j0, rest = tails ^ b0;
+      const bool two = rest != 0;
+      const uint32_t j1 = bfind32(two ? rest : b0);  // j0 again when it was the last one
+      tails = rest & ~(1u << j1);
+      const uint64_t w0 = lds_b64(wcol + j0 * wstride);
+      const uint64_t w1 = lds_b64(wcol + j1 * wstride);
+      float t0, t1;
+      float z0 = normal_tail_mid_f32(w0, t0), z1 = normal_tail_mid_f32(w1, t1);
+      if (fmaxf(t0, t1) > 25.0f) {  // far tail: essentially never
+        if (t0 > 25.0f) z0 = normal_tail_far_f32(w0, t0);
+        if (t1 > 25.0f) z1 = normal_tail_far_f32(w1, t1);
+      }
+      sts_f32(zcol + (j0 & (RING - 1)) * zstride + (j0 >> kLog) * 4, z0);
+      if (two) sts_f32(zcol + (j1 & (RING - 1)) * zstride + (j1 >> kLog) * 4, z1);
     }
   }
   static __device__ __forceinline__ void get(uint32_t addr, double& zv, double& zx) {
@@ -260,15 +311,15 @@ struct ZRing<HEXO_NORMAL_F64> {
   }
   static __device__ __forceinline__ void tail_phase(uint32_t tails, uint32_t wcol,
                                                     uint32_t wstride, uint32_t zcol,
-                                                    uint32_t zstride) {
+                                                    uint32_t zstride, uint32_t wplane = 8) {
     while (tails) {  // two tail draws per iteration, as in F32 mode
       const int j0 = __ffs(tails) - 1;
       tails &= tails - 1;
       const bool two = tails != 0;
       const int j1 = two ? __ffs(tails) - 1 : j0;
       tails &= tails - 1;
-      const uint64_t w0 = lds_b64(wcol + (j0 >> 1) * wstride + (j0 & 1) * 8);
-      const uint64_t w1 = lds_b64(wcol + (j1 >> 1) * wstride + (j1 & 1) * 8);
+      const uint64_t w0 = lds_b64(wcol + (j0 >> 1) * wstride + (j0 & 1) * wplane);
+      const uint64_t w1 = lds_b64(wcol + (j1 >> 1) * wstride + (j1 & 1) * wplane);
       double r0, r1;
       double z0 = normal_tail_mid_f64(w0, r0), z1 = normal_tail_mid_f64(w1, r1);
       if (fmax(r0, r1) > Ppnd::SPLIT2) {  // far tail: essentially never
@@ -277,6 +328,46 @@ struct ZRing<HEXO_NORMAL_F64> {
       }
       sts_f64(zcol + (j0 >> 1) * zstride + (j0 & 1) * 8, z0);
       if (two) sts_f64(zcol + (j1 >> 1) * zstride + (j1 & 1) * 8, z1);
+    }
+  }
+  template <int RING>
+  static __device__ __forceinline__ uint32_t central_round_planar(const uint64_t (&o)[16],
+                                                                  int step0, uint32_t zcol,
+                                                                  uint32_t zstride) {
+    static_assert(2 * RING <= 32 && (RING & (RING - 1)) == 0, "tail mask is 32 bits");
+    uint32_t tails = 0;
+#pragma unroll
+    for (int s = 0; s < kStepsPerRound; ++s) {
+      bool t0, t1;
+      const double zv = normal_central_f64(o[2 * s], t0);
+      const double zx = normal_central_f64(o[2 * s + 1], t1);
+      sts_f64x2(zcol + (step0 + s) * zstride, zv, zx);
+      if (t0) tails |= 1u << (step0 + s);
+      if (t1) tails |= 1u << (RING + step0 + s);
+    }
+    return tails;
+  }
+  template <int RING>
+  static __device__ __forceinline__ void tail_phase_planar(uint32_t tails, uint32_t wcol,
+                                                           uint32_t wstride, uint32_t zcol,
+                                                           uint32_t zstride) {
+    constexpr int kLog = RING == 16 ? 4 : RING == 8 ? 3 : RING == 4 ? 2 : 1;
+    while (tails) {
+      const uint32_t j0 = bfind32(tails);
+      const uint32_t b0 = 1u << j0, rest = tails ^ b0;
+      const bool two = rest != 0;
+      const uint32_t j1 = bfind32(two ? rest : b0);  // j0 again when it was the last one
+      tails = rest & ~(1u << j1);
+      const uint64_t w0 = lds_b64(wcol + j0 * wstride);
+      const uint64_t w1 = lds_b64(wcol + j1 * wstride);
+      double r0, r1;
+      double z0 = normal_tail_mid_f64(w0, r0), z1 = normal_tail_mid_f64(w1, r1);
+      if (fmax(r0, r1) > Ppnd::SPLIT2) {  // far tail: essentially never
+        if (r0 > Ppnd::SPLIT2) z0 = normal_tail_far_f64(w0, r0);
+        if (r1 > Ppnd::SPLIT2) z1 = normal_tail_far_f64(w1, r1);
+      }
+      sts_f64(zcol + (j0 & (RING - 1)) * zstride + (j0 >> kLog) * 8, z0);
+      if (two) sts_f64(zcol + (j1 & (RING - 1)) * zstride + (j1 >> kLog) * 8, z1);
     }
   }
   static __device__ __forceinline__ void get(uint32_t addr, double& zv, double& zx) {
@@ -343,8 +434,13 @@ heston_qe_paths_kernel(const __grid_constant__ PathArgs a) {
   unsigned char* sp = smem_raw;
   // pin32: keep the ring addresses in registers; otherwise ptxas re-derives them from
   // %tid / %ntid / the shared window base inside the step and tail loops (~20 instructions)
-  const uint32_t zstride = pin32(Ring::kBytesPerStep * T), ustride = pin32(16 * T);
-  const uint32_t ucol = pin32(smem_addr(sp) + 16 * tid);  // raw (variance, spot) words per step
+  // raw words in two planes, [variance words | spot words], each [kRing][T]: the two 64-bit
+  // stores of a step are not adjacent (adjacent, ptxas fuses them into one 128-bit store and
+  // pays four moves to line the words up in an aligned register quad) and a warp's 64-bit
+  // accesses touch consecutive 8-byte slots
+  const uint32_t zstride = pin32(Ring::kBytesPerStep * T), ustride = pin32(8 * T);
+  const uint32_t uplane = pin32(8 * kRing * T);
+  const uint32_t ucol = pin32(smem_addr(sp) + 8 * tid);  // variance word of step 0
   sp += (size_t)16 * kRing * T;
   const uint32_t zcol = pin32(smem_addr(sp) + Ring::kBytesPerStep * tid);
   sp += (size_t)Ring::kBytesPerStep * kRing * T;
@@ -389,11 +485,11 @@ heston_qe_paths_kernel(const __grid_constant__ PathArgs a) {
   auto park_round = [&](const uint64_t (&o)[16], int r) -> uint32_t {
     const uint32_t u0 = ucol + r * kStepsPerRound * ustride;
 #pragma unroll
-    for (int s = 0; s < kStepsPerRound; ++s) {  // two 64-bit stores: a 128-bit store would need
-      sts_b64(u0 + s * ustride, o[2 * s]);        // the four words moved into an aligned quad
-      sts_b64(u0 + s * ustride + 8, o[2 * s + 1]);
+    for (int s = 0; s < kStepsPerRound; ++s) {
+      sts_b64(u0 + s * ustride, o[2 * s]);
+      sts_b64(u0 + s * ustride + uplane, o[2 * s + 1]);
     }
-    return Ring::central_round(o, zcol + r * kStepsPerRound * zstride, zstride);
+    return Ring::template central_round_planar<kRing>(o, r * kStepsPerRound, zcol, zstride);
   };
   // refill the whole ring: kRing / 8 generator rounds, then ONE tail phase over all their draws
   auto refill = [&](uint64_t (&o)[16], bool have_first) {
@@ -401,9 +497,9 @@ heston_qe_paths_kernel(const __grid_constant__ PathArgs a) {
 #pragma unroll
     for (int r = 0; r < kRing / kStepsPerRound; ++r) {
       if (r > 0 || !have_first) rng.round(o);
-      tails |= park_round(o, r) << (16 * r);
+      tails |= park_round(o, r);
     }
-    Ring::tail_phase(tails, ucol, ustride, zcol, zstride);
+    Ring::template tail_phase_planar<kRing>(tails, ucol, ustride, zcol, zstride);
   };
   {
     uint64_t o[16];

@@ -67,7 +67,10 @@ __device__ __forceinline__ double qe_variance_quad(const SegConst& g, const doub
   const double me = fast_sqrt(fma(sw, dm, kFm.tiny));       // a b; sw dm >= 0, kept off exact 0
   mid.m = m;
   mid.s2h = s2h;
-  mid.rare = !(3.0 * w > s2h);                              // :63  psi >= 1.5
+  // :63  psi >= 1.5  <=>  3 w <= s^2/2.  Read off the sign of 3 w - s^2/2 on the integer pipe
+  // (the high word; a positive denormal counts as zero, where both branches are valid) instead of
+  // a multiply and a compare on the FP64 pipe.
+  mid.rare = __double2hiint(fma(3.0, w, -s2h)) <= 0;
   return fma(zv, fma(dm, zv, me + me), sw);                 // :64-68
 }
 
@@ -131,7 +134,11 @@ __device__ __forceinline__ double grow_spot_poly(const double X, const double de
   p = fma(p, delta, 1.0);
   return fma(X, p * delta, X);
 }
-__device__ __forceinline__ bool grow_spot_is_rare(const double delta) { return fabs(delta) > 0.08; }
+// |delta| > 0.08, tested on the high word (threshold 0.0799999982: the polynomial is as good
+// there) on the integer pipe
+__device__ __forceinline__ bool grow_spot_is_rare(const double delta) {
+  return (__double2hiint(delta) & 0x7fffffff) > 0x3fb47ae0;
+}
 __device__ __forceinline__ double grow_spot_rare(const double X, const double delta,
                                                  const uint32_t exptab_saddr) {
   return X * fast_exp(delta, exptab_saddr);
