@@ -50,6 +50,7 @@ class HexoPriceRequest(C.Structure):
         ("n_paths", C.c_uint64), ("steps", C.c_uint32), ("seed", C.c_uint64),
         ("normal_mode", C.c_int32), ("rng_mode", C.c_int32), ("n_streams", C.c_uint64),
         ("schedule_mode", C.c_int32), ("control_variate", C.c_int32),
+        ("drift_mode", C.c_int32),
     ]
 
 
@@ -137,7 +138,7 @@ def load() -> C.CDLL:
     lib.hexo_swift_price_chain.argtypes = [C.POINTER(HexoSwiftParams), C.POINTER(HexoHParams),
                                            C.c_double, C.c_double, C.c_double, c_double_p,
                                            C.c_uint32, c_double_p, c_double_p]
-    if lib.hexo_gpu_abi_version() != 2:
+    if lib.hexo_gpu_abi_version() != 3:
         raise ImportError("libhexo_gpu.so has an unexpected ABI version; rebuild it")
     _lib = lib
     return lib

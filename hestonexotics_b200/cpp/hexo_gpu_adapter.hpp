@@ -47,6 +47,7 @@ struct GpuPriceOptions {
   int rng_mode = HEXO_RNG_SHISHUA;        // the reference's generator; HEXO_RNG_PHILOX optional
   int schedule_mode = HEXO_SCHEDULE_REFERENCE;  // the reference's time grid, quirks included
   int control_variate = HEXO_CV_NONE;     // HEXO_CV_UNDERLYING: prices and errors use c = A_T - S
+  int drift_mode = HEXO_DRIFT_REFERENCE;  // HEXO_DRIFT_MARTINGALE: Andersen's K0* per step
   uint64_t n_streams = 0;                 // 0 = sized for the device(s)
   int n_gpus = 1;                         // devices of this process to spread over; 0 = all
   std::vector<ffloat>* stderr_out = nullptr;  // optional Monte-Carlo standard errors
@@ -86,6 +87,7 @@ std::vector<ffloat> price_gpu(const HParams& p, const ffloat S,
   req.rng_mode = opt.rng_mode;
   req.schedule_mode = opt.schedule_mode;
   req.control_variate = opt.control_variate;
+  req.drift_mode = opt.drift_mode;
   req.n_streams = opt.n_streams;
   std::vector<ffloat> prices(n_opts);
   if (opt.stderr_out) opt.stderr_out->assign(n_opts, 0.0);

@@ -158,7 +158,7 @@ __global__ void ppnd16_kernel(const double* in, double* out, size_t n) {
 // ---------------------------------------------------------------------------
 // K4: tape replay (one thread per path), same stepper and policy arithmetic
 // ---------------------------------------------------------------------------
-template <int PAYOFF>
+template <int PAYOFF, bool MART>
 __global__ void qe_replay_kernel(double v0, double S, double lnS, uint32_t n_seg,
                                  const SegConst* segs, const double* tape, uint64_t n_paths,
                                  uint32_t tape_steps, double* finals) {
@@ -179,8 +179,10 @@ __global__ void qe_replay_kernel(double v0, double S, double lnS, uint32_t n_seg
     double sumX = 0.0;
     for (uint32_t i = 0; i < n; ++i, ++step) {
       const double uv = t[3 * step + 1];
-      const double Vn = qe_variance(g, V, t[3 * step], [uv]() { return uv; });
-      const double delta = qe_logreturn(g, V, Vn, t[3 * step + 2]);
+      double k0 = 0.0;
+      const double Vn = qe_variance<MART>(g, V, t[3 * step], [uv]() { return uv; }, &k0);
+      const double delta = MART ? qe_logreturn_mart(g, V, Vn, t[3 * step + 2], k0)
+                                : qe_logreturn(g, V, Vn, t[3 * step + 2]);
       V = Vn;
       if (PAYOFF == HEXO_PAYOFF_ASIAN) {  // same arithmetic as the path kernel
         Xprev = X;
@@ -300,6 +302,8 @@ static int check_request(const hexo_price_request* r, bool need_strikes) {
     return fail(HEXO_ERR_INVALID_ARGUMENT, "unknown schedule_mode %d", r->schedule_mode);
   if (r->control_variate != HEXO_CV_NONE && r->control_variate != HEXO_CV_UNDERLYING)
     return fail(HEXO_ERR_INVALID_ARGUMENT, "unknown control_variate %d", r->control_variate);
+  if (r->drift_mode != HEXO_DRIFT_REFERENCE && r->drift_mode != HEXO_DRIFT_MARTINGALE)
+    return fail(HEXO_ERR_INVALID_ARGUMENT, "unknown drift_mode %d", r->drift_mode);
   // The reference divides by kappa and sigma (HSimulation.tpp:60,75-77) and takes log(S) (:90);
   // it would silently produce NaN prices.  Refuse instead.
   const hexo_hparams& p = r->p;
@@ -363,6 +367,9 @@ static int build_segments(const hexo_price_request* r, bool with_strikes,
     g.K1 = .5 * h * (kappa * rho / eps - .5) - rho / eps;               // :76
     g.K2 = .5 * h * (kappa * rho / eps - .5) + rho / eps;               // :77
     g.K3 = .5 * h * (1 - rho * rho);                                    // :78 (= K4, :79)
+    g.A = g.K2 + .5 * g.K3;  // HEXO_DRIFT_MARTINGALE (Andersen 2008, Prop. 9)
+    g.A2 = 2. * g.A;
+    g.K1m = -.5 * g.K3;
     g.first_opt = with_strikes ? r->strike_offsets[k] : 0;
     g.n_strikes = with_strikes ? r->strike_offsets[k + 1] - r->strike_offsets[k] : 0;
     g.pad = 0;
@@ -425,6 +432,7 @@ struct Plan {
   double* sums_dev = nullptr; // inside blob unless caller-supplied
   size_t gacc_bytes = 0;
   bool cv = false;  // control-variate sums (template parameter CV of the path kernel)
+  bool mart = false;  // HEXO_DRIFT_MARTINGALE (template parameter MART)
   bool ws = false;  // warp-specialised kernel (path_kernel_ws.cuh)
   bool il = false;  // interleaved look-ahead kernel (path_kernel_il.cuh)
 };
@@ -432,10 +440,13 @@ struct Plan {
 // The path-kernel instantiations live in their own translation units (path_kernels_*.cu), which
 // build in parallel; path_kernels.h declares the selectors.
 static PathKernel pick_kernel(int payoff, int normal_mode, uint32_t n_seg, int rng_mode = 0,
-                              bool cv = false) {
+                              bool cv = false, bool mart = false) {
   const int segs = n_seg == 1                       ? kSegsSingle
                    : n_seg <= (uint32_t)kInlineSegs ? kSegsInline
                                                     : kSegsGlobal;
+  if (mart)
+    return rng_mode == HEXO_RNG_PHILOX ? path_kernel_philox_mart(payoff, normal_mode, segs, cv)
+                                       : path_kernel_shishua_mart(payoff, normal_mode, segs, cv);
   if (rng_mode == HEXO_RNG_PHILOX) return path_kernel_philox(payoff, normal_mode, segs, cv);
   return cv ? path_kernel_shishua_cv(payoff, normal_mode, segs)
             : path_kernel_shishua(payoff, normal_mode, segs);
@@ -493,7 +504,8 @@ static int plan_create(const hexo_price_request* r, uint64_t stream_begin, uint6
     if (b >= 32 && b <= kMaxBlock && b % 32 == 0) block = b;
   }
   p->rng_mode = r->rng_mode;
-  const bool plain = r->rng_mode == HEXO_RNG_SHISHUA && !r->control_variate;
+  const bool plain = r->rng_mode == HEXO_RNG_SHISHUA && !r->control_variate &&
+                     r->drift_mode == HEXO_DRIFT_REFERENCE;
   const uint32_t n_sums = (uint32_t)sums_len(r);
   p->n_sums = n_sums;
   p->ws = plain && use_ws();  // the WS / IL experiments carry neither Philox nor the control variate
@@ -550,6 +562,7 @@ static int plan_create(const hexo_price_request* r, uint64_t stream_begin, uint6
   a.n_seg = r->n_chains;
   a.n_opts = n_opts;
   p->cv = r->control_variate != HEXO_CV_NONE;
+  p->mart = r->drift_mode == HEXO_DRIFT_MARTINGALE;
   a.segs = reinterpret_cast<const SegConst*>(base);
   for (size_t k = 0; k < segs.size() && k < (size_t)kInlineSegs; ++k) a.seg_inline[k] = segs[k];
   a.strikes = reinterpret_cast<const double*>(base + off_strikes);
@@ -567,7 +580,7 @@ static int plan_create(const hexo_price_request* r, uint64_t stream_begin, uint6
   } else {
     PathKernel kern = p->il ? pick_il_kernel(p->payoff, p->normal_mode, p->args.n_seg)
                             : pick_kernel(p->payoff, p->normal_mode, p->args.n_seg, p->rng_mode,
-                                           p->cv);
+                                           p->cv, p->mart);
     HEXO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem));
   }
   return HEXO_OK;
@@ -582,7 +595,7 @@ static int plan_launch(const Plan* p, cudaStream_t st, double* sums_out_dev) {
   } else {
     PathKernel kern = p->il ? pick_il_kernel(p->payoff, p->normal_mode, p->args.n_seg)
                             : pick_kernel(p->payoff, p->normal_mode, p->args.n_seg, p->rng_mode,
-                                           p->cv);
+                                           p->cv, p->mart);
     kern<<<p->grid, p->block, p->smem, st>>>(p->args);
   }
   HEXO_CUDA(cudaGetLastError());
@@ -1066,14 +1079,14 @@ int hexo_gpu_replay(const hexo_price_request* req, const double* tape, uint64_t 
   if (e == cudaSuccess) e = cudaMemcpy(dtape, tape, tape_bytes, cudaMemcpyHostToDevice);
   if (e == cudaSuccess) {
     const unsigned grid = (unsigned)((n_paths + 127) / 128);
-    if (req->payoff == HEXO_PAYOFF_ASIAN)
-      qe_replay_kernel<HEXO_PAYOFF_ASIAN><<<grid, 128>>>(req->p.v_0, req->S, log(req->S),
-                                                         req->n_chains, dseg, dtape, n_paths,
-                                                         tape_steps, dfin);
-    else
-      qe_replay_kernel<HEXO_PAYOFF_EUROPEAN><<<grid, 128>>>(req->p.v_0, req->S,
-                                                            log(req->S), req->n_chains, dseg, dtape,
-                                                            n_paths, tape_steps, dfin);
+    const bool mart = req->drift_mode == HEXO_DRIFT_MARTINGALE;
+    auto kern = req->payoff == HEXO_PAYOFF_ASIAN
+                    ? (mart ? qe_replay_kernel<HEXO_PAYOFF_ASIAN, true>
+                            : qe_replay_kernel<HEXO_PAYOFF_ASIAN, false>)
+                    : (mart ? qe_replay_kernel<HEXO_PAYOFF_EUROPEAN, true>
+                            : qe_replay_kernel<HEXO_PAYOFF_EUROPEAN, false>);
+    kern<<<grid, 128>>>(req->p.v_0, req->S, log(req->S), req->n_chains, dseg, dtape, n_paths,
+                        tape_steps, dfin);
     e = cudaGetLastError();
   }
   if (e == cudaSuccess) e = cudaMemcpy(finals_out, dfin, fin_bytes, cudaMemcpyDeviceToHost);

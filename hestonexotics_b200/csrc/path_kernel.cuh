@@ -421,7 +421,8 @@ __device__ __forceinline__ void accumulate_with_control(const double* fvbuf, uns
 // then reads at most two register pairs.
 enum : int { kSegsGlobal = 0, kSegsInline = 1, kSegsSingle = 2 };
 
-template <int PAYOFF, int NORMAL_MODE, int SEGS, class Gen = Shishua, bool CV = false>
+template <int PAYOFF, int NORMAL_MODE, int SEGS, class Gen = Shishua, bool CV = false,
+          bool MART = false>
 __global__ void __launch_bounds__(kMaxBlock, kMinBlocksPerSM)
 heston_qe_paths_kernel(const __grid_constant__ PathArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -538,8 +539,11 @@ heston_qe_paths_kernel(const __grid_constant__ PathArgs a) {
         // (X is needed every step, ln X never); European: ln X is accumulated and X = exp(ln X)
         // only where with_x says so (HSimulation.tpp:80-82)
         // keep_prev: remember X before the step (only the last step of a run needs it)
-        auto spot_half = [&](double Vfrom, double Vto, double zx, auto with_x, bool keep_prev) {
-          const double delta = qe_logreturn(g, Vfrom, Vto, zx);
+        // k0 (MART): -ln M of that step (HEXO_DRIFT_MARTINGALE)
+        auto spot_half = [&](double Vfrom, double Vto, double zx, double k0, auto with_x,
+                             bool keep_prev) {
+          const double delta = MART ? qe_logreturn_mart(g, Vfrom, Vto, zx, k0)
+                                    : qe_logreturn(g, Vfrom, Vto, zx);
           if (kAsian) {
             if (keep_prev) Xprev = X;
             X = grow_spot(X, delta, exptab_s);
@@ -557,6 +561,7 @@ heston_qe_paths_kernel(const __grid_constant__ PathArgs a) {
         // with_x: also X = exp(ln X) (HSimulation.tpp:81-82)
         auto run = [&](uint32_t count, auto with_x) {
           double Vold = V, zx_pend = 0.0;  // (V_{j-1}, Z_X of step j-1) of the pending half
+          double k0_pend = 0.0;            // MART: -ln M of step j-1
           bool first = true;
           while (count) {
             if (pos == kRing) {
@@ -575,7 +580,8 @@ heston_qe_paths_kernel(const __grid_constant__ PathArgs a) {
               double zv;
               Ring::get(za, zv, zx_pend);
               Vold = V;
-              V = qe_variance(g, Vold, zv, [ua]() { return u64_to_unit(lds_b64(ua)); });
+              V = qe_variance<MART>(g, Vold, zv, [ua]() { return u64_to_unit(lds_b64(ua)); },
+                                    &k0_pend);
               --m, za += zstride, ua += ustride;
             }
             // unrolled by two so that the loop-carried rotation (Vold <- V <- V', Z_X) becomes
@@ -589,16 +595,18 @@ heston_qe_paths_kernel(const __grid_constant__ PathArgs a) {
               // cases of both (|log-return| > 0.08; psi >= 1.5) share a single branch behind
               // them -- a branch per half would put a convergence barrier between the chains
               // and ptxas then runs them one after the other.
-              const double delta = qe_logreturn(g, Vold, V, zx_pend);
+              const double delta = MART ? qe_logreturn_mart(g, Vold, V, zx_pend, k0_pend)
+                                        : qe_logreturn(g, Vold, V, zx_pend);
               QeVarMid mid;
-              double Vn = qe_variance_quad(g, V, zv, mid);
+              double Vn = qe_variance_quad<MART>(g, V, zv, mid);
               if (kAsian) {
                 double Xn = grow_spot_poly(X, delta);
                 const bool rare_x = grow_spot_is_rare(delta);
                 if (rare_x | mid.rare) {
                   if (rare_x) Xn = grow_spot_rare(X, delta, exptab_s);
                   if (mid.rare)
-                    Vn = qe_variance_rare(mid, [ua]() { return u64_to_unit(lds_b64(ua)); });
+                    Vn = qe_variance_rare<MART>(g, V, mid,
+                                                [ua]() { return u64_to_unit(lds_b64(ua)); });
                 }
                 X = Xn;
                 sumX += X;
@@ -609,15 +617,17 @@ heston_qe_paths_kernel(const __grid_constant__ PathArgs a) {
                   X = fast_exp(lnX, exptab_s);
                 }
                 if (mid.rare)
-                  Vn = qe_variance_rare(mid, [ua]() { return u64_to_unit(lds_b64(ua)); });
+                  Vn = qe_variance_rare<MART>(g, V, mid,
+                                              [ua]() { return u64_to_unit(lds_b64(ua)); });
               }
               Vold = V;
               V = Vn;
               zx_pend = zx;
+              if (MART) k0_pend = mid.k0;
             }
           }
           // epilogue: second half of the last step
-          spot_half(Vold, V, zx_pend, with_x, true);
+          spot_half(Vold, V, zx_pend, k0_pend, with_x, true);
         };
         if (kAsian) {
           if (n > 0) run(n, std::true_type{});

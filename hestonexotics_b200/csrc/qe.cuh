@@ -39,6 +39,9 @@ struct SegConst {
   double m0;        // theta (1 - D):  m = V D + m0                        (:59)
   double c1h, c2h;  // s^2/2 = |V c1h + c2h|                               (:60)
   double K0, K1, K2, K3;  // K4 == K3 because gamma_1 == gamma_2           (:75-79)
+  // HEXO_DRIFT_MARTINGALE only: A = K2 + K4/2 and its double, and -K3/2, the factor of V that
+  // is left of K1 V once K0* = -ln M - (K1 + K3/2) V takes the place of K0
+  double A, A2, K1m;
   uint32_t n_steps, first_opt, n_strikes, pad;
 };
 
@@ -54,9 +57,12 @@ struct SegConst {
 struct QeVarMid {
   double m, s2h;  // :59, :60 (s^2/2)
   bool rare;      // psi >= 1.5: the quadratic value has to be replaced by qe_variance_rare
+  double k0;      // MART only: K0* + (K1 + K3/2) V = -ln M of this step
 };
 
 // quadratic branch, evaluated unconditionally (NaN when psi > 2; replaced where mid.rare)
+//   MART: also mid.k0 = -ln M = -(A sw / (1 - 2 A dm)) + ln(1 - 2 A dm) / 2   (a b^2 = sw, a = dm)
+template <bool MART = false>
 __device__ __forceinline__ double qe_variance_quad(const SegConst& g, const double V,
                                                    const double zv, QeVarMid& mid) {
   const double m = fma(V, g.D, g.m0);                       // :59
@@ -71,6 +77,12 @@ __device__ __forceinline__ double qe_variance_quad(const SegConst& g, const doub
   // (the high word; a positive denormal counts as zero, where both branches are valid) instead of
   // a multiply and a compare on the FP64 pipe.
   mid.rare = __double2hiint(fma(3.0, w, -s2h)) <= 0;
+  if (MART) {
+    const double d = fma(-g.A2, dm, 1.0);                   // 1 - 2 A a
+    const double k0 = fma(0.5, fast_log(d), -(g.A * sw) * fast_rcp(d));
+    // M does not exist for 1 - 2 A a <= 0: keep the reference drift K0 + (K1 + K3/2) V
+    mid.k0 = d > 0.0 ? k0 : fma(g.K1 - g.K1m, V, g.K0);
+  }
   return fma(zv, fma(dm, zv, me + me), sw);                 // :64-68
 }
 
@@ -80,8 +92,10 @@ __device__ __forceinline__ double qe_variance_quad(const SegConst& g, const doub
 //   beta = 2/(m (psi+1)) = 2 m / q,  1 - p = 2 m^2 / q
 //   V' = ln((1-p)/(1-U)) / beta = q/(2m) ln(2 m^2 / (q (1-U)))
 //   uv : callable returning the variance UNIFORM of the same draw
-template <class UniformFn>
-__device__ __forceinline__ double qe_variance_rare(const QeVarMid& mid, const UniformFn& uv) {
+//   MART: mid.k0 = -ln M,  M = p + beta (1-p) / (beta - A) = ((s^2 - m^2) + 4 m^3 / (2 m - A q)) / q
+template <bool MART = false, class UniformFn>
+__device__ __forceinline__ double qe_variance_rare(const SegConst& g, const double V, QeVarMid& mid,
+                                                   const UniformFn& uv) {
   const double m = mid.m;
   const double m2 = m * m, s2 = mid.s2h + mid.s2h;
   const double q = m2 + s2;
@@ -95,18 +109,25 @@ __device__ __forceinline__ double qe_variance_rare(const QeVarMid& mid, const Un
     const double y = (m2 + m2) * fast_rcp(q * (1.0 - u));
     v = 0.5 * q * fast_rcp(m) * fast_log(y);
   }
+  if (MART) {
+    const double d = fma(-g.A, q, m + m);                   // (beta - A) q
+    const double M = ((s2 - m2) + 4.0 * m2 * m * fast_rcp(d)) * fast_rcp(q);
+    mid.k0 = d > 0.0 ? -fast_log(M) : fma(g.K1 - g.K1m, V, g.K0);
+  }
   return v;
 }
 
 // Variance half, src/HSimulation.tpp:59-73.
 //   zv : variance normal (used when psi < 1.5)
 //   uv : callable returning the variance UNIFORM of the same draw (psi >= 1.5)
-template <class UniformFn>
+//   k0 (MART): receives -ln M of the step
+template <bool MART = false, class UniformFn>
 __device__ __forceinline__ double qe_variance(const SegConst& g, const double V, const double zv,
-                                              const UniformFn& uv) {
+                                              const UniformFn& uv, double* k0 = nullptr) {
   QeVarMid mid;
-  double Vn = qe_variance_quad(g, V, zv, mid);
-  if (mid.rare) Vn = qe_variance_rare(mid, uv);
+  double Vn = qe_variance_quad<MART>(g, V, zv, mid);
+  if (mid.rare) Vn = qe_variance_rare<MART>(g, V, mid, uv);
+  if (MART) *k0 = mid.k0;
   return Vn;
 }
 
@@ -118,6 +139,13 @@ __device__ __forceinline__ double qe_logreturn(const SegConst& g, const double V
   // rsqrt seed finite and changes nothing otherwise
   const double sq = fast_sqrt(fma(g.K3, V + Vn, kFm.tiny));
   return fma(sq, zx, fma(g.K2, Vn, fma(g.K1, V, g.K0)));
+}
+// HEXO_DRIFT_MARTINGALE: K0* + K1 V = k0 - (K3/2) V with k0 = -ln M of the step
+__device__ __forceinline__ double qe_logreturn_mart(const SegConst& g, const double V,
+                                                    const double Vn, const double zx,
+                                                    const double k0) {
+  const double sq = fast_sqrt(fma(g.K3, V + Vn, kFm.tiny));
+  return fma(sq, zx, fma(g.K2, Vn, fma(g.K1m, V, k0)));
 }
 
 // X' = exp(ln X + delta) (HSimulation.tpp:82) as X e^delta.  One-step log-returns are

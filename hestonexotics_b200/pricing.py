@@ -43,6 +43,7 @@ _NORMAL_MODES = {"f32": _lib.NORMAL_F32, "as-built": _lib.NORMAL_F32, "f64": _li
 _RNG_MODES = {"shishua": 0, "philox": 1, 0: 0, 1: 1}   # hexo_rng_mode
 _GRID_MODES = {"reference": 0, "exact": 1, 0: 0, 1: 1}  # hexo_schedule_mode
 _CV_MODES = {None: 0, "none": 0, "underlying": 1, 0: 0, 1: 1}  # hexo_control_variate
+_DRIFT_MODES = {"reference": 0, "martingale": 1, 0: 0, 1: 1}  # hexo_drift_mode
 
 
 @dataclass
@@ -64,7 +65,8 @@ class _Request:
 
     def __init__(self, scheme, p: HParams, S: float, all_chains: Sequence[OptionsChain],
                  n_simulations: int, n_opts: Optional[int], steps: int, seed: int, normal_mode,
-                 n_streams: int, rng="shishua", time_grid="reference", control_variate=None):
+                 n_streams: int, rng="shishua", time_grid="reference", control_variate=None,
+                 drift="reference"):
         if isinstance(scheme, type) and hasattr(scheme, "payoff"):
             scheme = HQEAnderson(scheme)
         self.expiries, self.offsets, self.strikes = flatten_chains(all_chains)
@@ -80,13 +82,16 @@ class _Request:
             raise ValueError(f"time_grid must be 'reference' or 'exact', got {time_grid!r}")
         if control_variate not in _CV_MODES:
             raise ValueError(f"control_variate must be None or 'underlying', got {control_variate!r}")
+        if drift not in _DRIFT_MODES:
+            raise ValueError(f"drift must be 'reference' or 'martingale', got {drift!r}")
         self.req = _lib.HexoPriceRequest(
             _lib.HexoHParams(*p.as_tuple()), float(S), scheme.payoff, len(self.expiries),
             self.expiries.ctypes.data_as(_lib.c_double_p),
             self.offsets.ctypes.data_as(_lib.c_uint32_p),
             self.strikes.ctypes.data_as(_lib.c_double_p),
             int(n_simulations), int(steps), int(seed), _NORMAL_MODES[normal_mode],
-            _RNG_MODES[rng], int(n_streams), _GRID_MODES[time_grid], _CV_MODES[control_variate])
+            _RNG_MODES[rng], int(n_streams), _GRID_MODES[time_grid], _CV_MODES[control_variate],
+            _DRIFT_MODES[drift])
         self.n_sums = 3 * self.n_opts + 2 * len(self.expiries) if self.req.control_variate \
             else 2 * self.n_opts
 
@@ -108,14 +113,14 @@ def _finish(rq: "_Request", sums: np.ndarray):
 def price_full(scheme, p: HParams, S: float, all_chains: Sequence[OptionsChain],
                n_simulations: int, n_opts: Optional[int], steps: int, *, seed: int = 1,
                normal_mode="f32", n_streams: int = 0, rng="shishua",
-               time_grid="reference", control_variate=None,
+               time_grid="reference", control_variate=None, drift="reference",
                device: Optional[int] = None) -> PriceResult:
     """price<Scheme>() on one GPU, returning prices, standard errors and launch statistics."""
     lib = _lib.load()
     if device is not None:
         _lib.check(lib.hexo_gpu_init(int(device)))
     rq = _Request(scheme, p, S, all_chains, n_simulations, n_opts, steps, seed, normal_mode,
-                  n_streams, rng, time_grid, control_variate)
+                  n_streams, rng, time_grid, control_variate, drift)
     if rq.req.n_streams == 0:
         rq.req.n_streams = lib.hexo_gpu_default_streams(rq.req.n_paths, rq.n_opts, 1)
     sums = np.zeros(rq.n_sums, dtype=np.float64)
@@ -131,12 +136,12 @@ def price_full(scheme, p: HParams, S: float, all_chains: Sequence[OptionsChain],
 def price_multi(scheme, p: HParams, S: float, all_chains: Sequence[OptionsChain],
                 n_simulations: int, n_opts: Optional[int], steps: int, *, n_gpus: int = 0,
                 seed: int = 1, normal_mode="f32", n_streams: int = 0, rng="shishua",
-                time_grid="reference", control_variate=None):
+                time_grid="reference", control_variate=None, drift="reference"):
     """price<Scheme>() spread over several GPUs of THIS process (hexo_gpu_price_multi); returns
     (prices, stderr).  n_gpus = 0 uses every visible device."""
     lib = _lib.load()
     rq = _Request(scheme, p, S, all_chains, n_simulations, n_opts, steps, seed, normal_mode,
-                  n_streams, rng, time_grid, control_variate)
+                  n_streams, rng, time_grid, control_variate, drift)
     prices, se = np.zeros(rq.n_opts), np.zeros(rq.n_opts)
     _lib.check(lib.hexo_gpu_price_multi(C.byref(rq.req), int(n_gpus),
                                         prices.ctypes.data_as(_lib.c_double_p),
@@ -147,7 +152,7 @@ def price_multi(scheme, p: HParams, S: float, all_chains: Sequence[OptionsChain]
 def price_batch(scheme, params: Sequence[HParams], S: float, all_chains: Sequence[OptionsChain],
                 n_simulations: int, n_opts: Optional[int], steps: int, *, seeds=1,
                 normal_mode="f32", n_streams: int = 0, rng="shishua", time_grid="reference",
-                control_variate=None, n_lanes: int = 0):
+                control_variate=None, drift="reference", n_lanes: int = 0):
     """price<Scheme>() of the same chains for MANY parameter sets in one submission
     (hexo_gpu_price_batch): the shape of Monte-Carlo pricing inside a calibration loop.  `seeds`
     is one seed for all jobs (common random numbers) or one per parameter set.  Returns
@@ -160,7 +165,8 @@ def price_batch(scheme, params: Sequence[HParams], S: float, all_chains: Sequenc
     if len(seeds) != len(params):
         raise ValueError("one seed per parameter set")
     rqs = [_Request(scheme, p, S, all_chains, n_simulations, n_opts, steps, sd, normal_mode,
-                    n_streams, rng, time_grid, control_variate) for p, sd in zip(params, seeds)]
+                    n_streams, rng, time_grid, control_variate, drift)
+           for p, sd in zip(params, seeds)]
     arr = (_lib.HexoPriceRequest * len(rqs))(*[r.req for r in rqs])
     n = rqs[0].n_opts
     prices, se = np.zeros((len(rqs), n)), np.zeros((len(rqs), n))
@@ -187,7 +193,7 @@ def shard_range(n_streams: int, rank: int, world_size: int):
 def price_distributed(scheme, p: HParams, S: float, all_chains: Sequence[OptionsChain],
                       n_simulations: int, n_opts: Optional[int], steps: int, *, seed: int = 1,
                       normal_mode="f32", n_streams: int = 0, rng="shishua",
-                      time_grid="reference", control_variate=None, group=None,
+                      time_grid="reference", control_variate=None, drift="reference", group=None,
                       _shard_sums=None) -> PriceResult:
     """price<Scheme>() sharded over the ranks of a torch.distributed group.
 
@@ -203,7 +209,7 @@ def price_distributed(scheme, p: HParams, S: float, all_chains: Sequence[Options
 
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     rq = _Request(scheme, p, S, all_chains, n_simulations, n_opts, steps, seed, normal_mode,
-                  n_streams, rng, time_grid, control_variate)
+                  n_streams, rng, time_grid, control_variate, drift)
     stats = _lib.HexoGpuStats()
     if _shard_sums is None:
         lib = _lib.load()

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define HEXO_GPU_ABI_VERSION 2 /* 2: rng_mode, schedule_mode, control_variate in the request */
+#define HEXO_GPU_ABI_VERSION 3 /* 2: rng_mode, schedule_mode, control_variate; 3: drift_mode */
 
 typedef enum {
   HEXO_OK = 0,
@@ -75,6 +75,17 @@ typedef enum { HEXO_SCHEDULE_REFERENCE = 0, HEXO_SCHEDULE_EXACT = 1 } hexo_sched
  * per maturity (hexo_gpu_sums_len). */
 typedef enum { HEXO_CV_NONE = 0, HEXO_CV_UNDERLYING = 1 } hexo_control_variate;
 
+/* Drift of the log-spot step.  REFERENCE is the reference's (HSimulation.tpp:75-80): the constant
+ * K0 of Andersen's scheme, under which the simulated spot is only approximately a martingale
+ * (SURVEY finding 7).  MARTINGALE replaces K0 step by step with Andersen's K0* (L. Andersen,
+ * "Simple and efficient simulation of the Heston stochastic volatility model", 2008, Prop. 9):
+ *   K0* = -ln M - (K1 + K3/2) V,   M = E[exp(A V') | V],   A = K2 + K4/2,
+ *   psi <  1.5:  M = exp(A b^2 a / (1 - 2 A a)) / sqrt(1 - 2 A a)
+ *   psi >= 1.5:  M = p + beta (1 - p) / (beta - A)
+ * so that E[X' | X, V] = X exactly and E[X_t] = S on every grid.  Where M does not exist
+ * (A >= 1/(2a) resp. A >= beta; not reachable with rho <= 0) the step keeps the reference drift. */
+typedef enum { HEXO_DRIFT_REFERENCE = 0, HEXO_DRIFT_MARTINGALE = 1 } hexo_drift_mode;
+
 /* HParams, src/inc/HDistribution.h:9-24 -- same field order, same meaning */
 typedef struct {
   double v_0;   /* initial variance            */
@@ -109,6 +120,7 @@ typedef struct {
                                   /* sharded over GPUs.                         */
   int32_t schedule_mode;          /* hexo_schedule_mode; 0 = the reference's    */
   int32_t control_variate;        /* hexo_control_variate; 0 = none             */
+  int32_t drift_mode;             /* hexo_drift_mode; 0 = the reference's       */
 } hexo_price_request;
 
 typedef struct {

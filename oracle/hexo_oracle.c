@@ -350,7 +350,9 @@ static double final_payoff(const policy *o, double strike) {
 }
 
 /* HQEAnderson::operator++, src/HSimulation.tpp:52-86 */
-static void qe_step(const oracle_hparams *p, sde_state *st, const policy *o, draw_src *d) {
+/* drift_mode 0 is the reference; 1 swaps K_0 for Andersen's K0* (oracle_qe_k0_star below) */
+static void qe_step_drift(const oracle_hparams *p, sde_state *st, const policy *o, draw_src *d,
+                          int drift_mode) {
   const double theta = p->v_m, rho = p->rho, kappa = p->kappa, eps = p->sigma; /* :54 */
   double delta = o->init_step_size;                                           /* :55 */
   double gamma_1 = .5, gamma_2 = .5;                                          /* :56-57 */
@@ -377,6 +379,8 @@ static void qe_step(const oracle_hparams *p, sde_state *st, const policy *o, dra
   double K_2 = gamma_2 * delta * (kappa * rho / eps - .5) + rho / eps;        /* :77 */
   double K_3 = gamma_1 * delta * (1 - rho * rho);                             /* :78 */
   double K_4 = gamma_2 * delta * (1 - rho * rho);                             /* :79 */
+  if (drift_mode == 1) /* NOT the reference: Andersen's K0* in place of K0 */
+    K_0 = oracle_qe_k0_star(p, delta, st->prev_V, NULL, NULL);
   st->log_X = st->log_X + K_0 + K_1 * st->prev_V + K_2 * st->cur_V +
               sqrt(K_3 * st->prev_V + K_4 * st->cur_V) * d->spot_normal(d);   /* :80 */
   st->prev_X = st->cur_X;                                                     /* :81 */
@@ -384,6 +388,39 @@ static void qe_step(const oracle_hparams *p, sde_state *st, const policy *o, dra
   st->prev_time = st->cur_time;                                               /* :83 */
   st->cur_time += delta;                                                      /* :84 */
   d->end_step(d);
+}
+
+/* Andersen (2008), Proposition 9, written with the scheme's own quantities a, b^2, p, beta
+ * (HSimulation.tpp:59-71); gamma_1 = gamma_2 = 1/2.  Not part of the reference. */
+double oracle_qe_k0_star(const oracle_hparams *p, double h, double V, int *branch, int *corrected) {
+  const double theta = p->v_m, rho = p->rho, kappa = p->kappa, eps = p->sigma;
+  const double discount = exp(-kappa * h);
+  const double m = theta + (V - theta) * discount;
+  const double sp2 = fabs(V * eps * eps * discount / kappa * (1 - discount) +
+                          theta * eps * eps / (2 * kappa) * (1. - discount) * (1. - discount));
+  const double Psi = sp2 / (m * m);
+  const double K_0 = -rho * kappa * theta / eps * h;
+  const double K_1 = .5 * h * (kappa * rho / eps - .5) - rho / eps;
+  const double K_2 = .5 * h * (kappa * rho / eps - .5) + rho / eps;
+  const double K_3 = .5 * h * (1 - rho * rho), K_4 = K_3;
+  const double A = K_2 + .5 * K_4;
+  double lnM;
+  int ok;
+  if (Psi < PSI_C) {
+    const double bp2 = 2 / Psi - 1 + sqrt(2 / Psi * (2 / Psi - 1));
+    const double a = m / (1 + bp2);
+    ok = 1 - 2 * A * a > 0;
+    lnM = ok ? A * bp2 * a / (1 - 2 * A * a) - .5 * log(1 - 2 * A * a) : 0;
+    if (branch) *branch = 0;
+  } else {
+    const double pp = (Psi - 1) / (Psi + 1);
+    const double beta = 2 / (m * (Psi + 1));
+    ok = beta > A;
+    lnM = ok ? log(pp + beta * (1 - pp) / (beta - A)) : 0;
+    if (branch) *branch = 1;
+  }
+  if (corrected) *corrected = ok;
+  return ok ? -lnM - (K_1 + .5 * K_3) * V : K_0;
 }
 
 typedef void (*pay_fn)(void *ctx, uint32_t chain, const policy *o);
@@ -404,7 +441,7 @@ static uint32_t simulate_path(const oracle_contract *c, draw_src *d, int trailin
   /* heston_sde = initial_state: HSimulation.tpp:26, :87-94 */
   sde_state st = {c->S, c->p.v_0, c->S, c->p.v_0, 0.0, 0.0, log(c->S)};
   if (n_opts == 0) return 0;
-  qe_step(&c->p, &st, &o, d);                                       /* :35 ++(sde=init) */
+  qe_step_drift(&c->p, &st, &o, d, c->drift_mode);                  /* :35 ++(sde=init) */
   n_steps = 1;
   for (;;) {
     while (st.cur_time >= c->expiries[chain] && opts_priced < n_opts) { /* :36, SDE.h:30 */
@@ -418,10 +455,10 @@ static uint32_t simulate_path(const oracle_contract *c, draw_src *d, int trailin
     }
     accumulate_value(&o, &st);                                      /* :44 */
     if (opts_priced >= n_opts) {
-      if (trailing_step) qe_step(&c->p, &st, &o, d);                /* :35 ++sde, then exit */
+      if (trailing_step) qe_step_drift(&c->p, &st, &o, d, c->drift_mode); /* :35 ++sde, exit */
       break;
     }
-    qe_step(&c->p, &st, &o, d);                                     /* :35 ++sde */
+    qe_step_drift(&c->p, &st, &o, d, c->drift_mode);                /* :35 ++sde */
     ++n_steps;
   }
   return n_steps;
@@ -547,7 +584,7 @@ static uint32_t simulate_path_exact(const oracle_contract *c, draw_src *d, pay_f
     o.init_step_size = span / (double)n; /* qe_step reads its step width here */
     o.earliest_unpriced_expi = c->expiries[k];
     for (long long j = 0; j < n; ++j) {
-      qe_step(&c->p, &st, &o, d);
+      qe_step_drift(&c->p, &st, &o, d, c->drift_mode);
       integral += o.init_step_size * .5 * (st.cur_X + st.prev_X);
       ++total;
     }

@@ -47,6 +47,9 @@ typedef struct {
   const uint32_t *strike_offsets; /* [n_chains+1] prefix sums of chain sizes */
   const double *strikes;          /* [n_opts] chain-major */
   uint32_t steps;                 /* the reference's `steps` argument */
+  int32_t drift_mode;             /* 0 = the reference's K0; 1 = Andersen's martingale-corrected
+                                     K0* (NOT in the reference; include/hexo_gpu.h,
+                                     HEXO_DRIFT_MARTINGALE) */
 } oracle_contract;
 
 /* ---- shishua (oracle/shishua.h) ------------------------------------------ */
@@ -126,6 +129,12 @@ int oracle_replay(const oracle_contract *c, const double *tape, uint64_t n_paths
 /* number of stepper invocations a path needs until its last maturity is paid
  * (excludes the reference's trailing extra `++`, HSimulation.tpp:35) */
 uint32_t oracle_steps_to_last_expiry(const oracle_contract *c);
+
+/* ---- martingale correction (not in the reference) --------------------------------------------
+ * K0* of one step of width h from variance V (Andersen 2008, Prop. 9), the constant term that
+ * replaces K0 in HSimulation.tpp:80 when drift_mode = 1.  *branch = 0 quadratic, 1 exponential;
+ * *corrected = 0 when M does not exist and the step keeps the reference drift. */
+double oracle_qe_k0_star(const oracle_hparams *p, double h, double V, int *branch, int *corrected);
 
 #ifdef __cplusplus
 }

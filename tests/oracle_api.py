@@ -31,7 +31,7 @@ class OracleHParams(C.Structure):
 class OracleContract(C.Structure):
     _fields_ = [("p", OracleHParams), ("S", C.c_double), ("payoff", C.c_int32),
                 ("n_chains", C.c_uint32), ("expiries", dp), ("strike_offsets", u32p),
-                ("strikes", dp), ("steps", C.c_uint32)]
+                ("strikes", dp), ("steps", C.c_uint32), ("drift_mode", C.c_int32)]
 
 
 def build_oracle():
@@ -82,8 +82,20 @@ def oracle() -> C.CDLL:
         o.oracle_replay.argtypes = [C.POINTER(OracleContract), dp, C.c_uint64, C.c_uint32, dp]
         o.oracle_steps_to_last_expiry.restype = C.c_uint32
         o.oracle_steps_to_last_expiry.argtypes = [C.POINTER(OracleContract)]
+        o.oracle_qe_k0_star.restype = C.c_double
+        o.oracle_qe_k0_star.argtypes = [C.POINTER(OracleHParams), C.c_double, C.c_double,
+                                        C.POINTER(C.c_int), C.POINTER(C.c_int)]
         _oracle = o
     return _oracle
+
+
+def k0_star(params, h, V):
+    """Andersen's martingale-corrected K0* of one step (oracle_qe_k0_star):
+    (K0*, branch 0 quadratic / 1 exponential, corrected flag)."""
+    hp = OracleHParams(*[float(x) for x in params])
+    br, ok = C.c_int(), C.c_int()
+    k0 = oracle().oracle_qe_k0_star(C.byref(hp), float(h), float(V), C.byref(br), C.byref(ok))
+    return float(k0), int(br.value), bool(ok.value)
 
 
 def have_ref() -> bool:
@@ -106,7 +118,8 @@ def ref() -> C.CDLL:
 class Contract:
     """Owns the numpy buffers an oracle_contract points to."""
 
-    def __init__(self, payoff, expiries, strikes_per_chain, steps, params=DEFAULT_PARAMS, S=100.0):
+    def __init__(self, payoff, expiries, strikes_per_chain, steps, params=DEFAULT_PARAMS, S=100.0,
+                 drift_mode=0):
         self.payoff = int(payoff)
         self.params = tuple(float(x) for x in params)
         self.S = float(S)
@@ -122,7 +135,7 @@ class Contract:
         self.c = OracleContract(OracleHParams(*self.params), self.S, self.payoff,
                                 len(self.expiries), self.expiries.ctypes.data_as(dp),
                                 self.offsets.ctypes.data_as(u32p), self.strikes.ctypes.data_as(dp),
-                                self.steps)
+                                self.steps, int(drift_mode))
 
     # ---- oracle entry points -------------------------------------------------
     def steps_to_last_expiry(self) -> int:

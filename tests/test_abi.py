@@ -32,7 +32,7 @@ def test_library_exports_every_declared_symbol(hexo_lib):
     assert host == sorted(_lib.HOST_SYMBOLS)
     for n in host:
         assert hasattr(hexo_lib, n), f"{n} declared in include/hexo_gpu.h but not exported"
-    assert hexo_lib.hexo_gpu_abi_version() == 2
+    assert hexo_lib.hexo_gpu_abi_version() == 3
 
 
 def test_struct_layout_matches_header(hexo_lib):
@@ -40,7 +40,7 @@ def test_struct_layout_matches_header(hexo_lib):
     assert [f[0] for f in _lib.HexoHParams._fields_] == ["v_0", "v_m", "rho", "kappa", "sigma"]
     assert C.sizeof(_lib.HexoHParams) == 40
     assert C.sizeof(_lib.HexoSegment) == 32
-    assert C.sizeof(_lib.HexoPriceRequest) == 40 + 8 + 8 + 24 + 8 + 8 + 8 + 8 + 8 + 8
+    assert C.sizeof(_lib.HexoPriceRequest) == 40 + 8 + 8 + 24 + 8 + 8 + 8 + 8 + 8 + 8 + 8
 
 
 @pytest.mark.parametrize("expiries,steps", [
