@@ -12,11 +12,12 @@ p = hx.HParams(0.04, 0.04, -0.7, 2.0, 0.5)
 stiff = hx.HParams(0.04, 0.04, -0.95, 20.0, 1.0)
 A = hx.HQEAnderson(hx.AAsianCallNonAdaptive); E = hx.HQEAnderson(hx.EuropeanCallNonAdaptive)
 scale = float(sys.argv[1]) if len(sys.argv) > 1 else 1.0
-def run(name, scheme, T, K, n, steps, mode, p=p, rng="shishua", reps=3):
+def run(name, scheme, T, K, n, steps, mode, p=p, rng="shishua", reps=3, drift="reference"):
     ch = [hx.OptionsChain.from_strikes(t, k) for t, k in zip(T, K)]
     best = None
     for i in range(reps):
-        r = hx.price_full(scheme, p, 100.0, ch, n, None, steps, seed=1 + i, normal_mode=mode, rng=rng)
+        r = hx.price_full(scheme, p, 100.0, ch, n, None, steps, seed=1, normal_mode=mode, rng=rng,
+                          drift=drift)
         if i and (best is None or r.kernel_ms < best.kernel_ms): best = r
     r = best
     print(f"{name:24s} {mode} {rng:7s} n={n:.0e} steps={steps:4d} ms={r.kernel_ms:8.2f} "
@@ -29,3 +30,5 @@ run("cfg5 stiff 2520", A, [10.0], [list(np.linspace(70,130,64))], int(2e6*scale)
 run("cfg3 chain 64x8", A, [0.25*k for k in range(1,9)], [list(np.linspace(70,130,64))]*8, int(2e6*scale), 252, "f32")
 run("cfg4 asian 1024", A, [1.0], [[100.0]], int(2e7*scale), 1024, "f64")
 run("cfg4 asian 1024", A, [1.0], [[100.0]], int(2e7*scale), 1024, "f32", rng="philox")
+run("cfg4 asian martingale", A, [1.0], [[100.0]], int(2e7*scale), 1024, "f32", drift="martingale")
+run("cfg1 asian 100k", A, [1.0], [[100.0]], 100_000, 252, "f32", reps=4)

@@ -23,5 +23,11 @@ for scheme in (A, E):
     r = hx.price_full(scheme, p, 100.0, many, 500, None, 6, n_streams=257, control_variate="underlying")
     r = hx.price_full(scheme, p, 100.0, one, 500, None, 6, n_streams=100, control_variate="underlying")
     r = hx.price_full(scheme, p, 100.0, wide, 300, None, 4, n_streams=64, control_variate="underlying")
+    for rng in ("shishua", "philox"):                                         # martingale drift
+        r = hx.price_full(scheme, p, 100.0, one, 700, None, 20, n_streams=300, rng=rng,
+                          drift="martingale")
+        r = hx.price_full(scheme, p, 100.0, many, 500, None, 6, n_streams=257, rng=rng,
+                          drift="martingale", control_variate="underlying", time_grid="exact")
+        assert np.isfinite(r.prices).all()
 pr, se, ms = hx.price_batch(A, [p, p, p], 100.0, one, 500, None, 10, n_lanes=2)
 print("sanitize probe ok", r.prices[:2], pr[:, 0])
