@@ -259,7 +259,7 @@ def run_ours(args):
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
     e2e_value = path_steps * args.e2e_steps / float(dt[0])
     h2d = rq.expiries.nbytes + rq.offsets.nbytes + rq.strikes.nbytes + C.sizeof(rq.req) \
-        + 120 * len(rq.expiries)            # request, flattened chains, segment constants
+        + 144 * len(rq.expiries)            # request, flattened chains, segment constants
     d2h = 2 * n_opts * 8
 
     if rank == 0:
@@ -293,9 +293,9 @@ def run_ours(args):
                 "unit": "TFLOP/s", "frac": achieved / fl.value,
                 # dram__bytes_read.sum + dram__bytes_write.sum of the path kernel in the round-1
                 # `ncu --set full` capture (profiles/r01_path_kernel_ncu_raw_final.csv, a
-                # 4.1e9-path-step launch): 60 928 B read, 0 B written -- code and constants only,
-                # it does not grow with the number of paths
-                "traffic": 73728,
+                # 4.1e9-path-step launch): 469 248 B read, 0 B written -- code and constants only
+                # (61 KB ... 469 KB from capture to capture), it does not grow with the paths
+                "traffic": 469248,
                 "note": "achieved = 100 algorithmic FP64 flop per path-step (SURVEY 8d) x path-steps "
                         "of one GPU / mean path-kernel time (CUDA events); peak = DFMA peak measured "
                         "in this run (hexo_gpu_measure_fp64_peak; MEASURED_PEAKS.json has no FP64 "
