@@ -481,8 +481,17 @@ static int plan_destroy(Plan* p, cudaStream_t st) {
   return HEXO_OK;
 }
 
+static int plan_fill(const hexo_price_request* r, uint64_t stream_begin, uint64_t stream_count,
+                     cudaStream_t st, Plan* p);
+// builds the plan; on failure nothing stays allocated
 static int plan_create(const hexo_price_request* r, uint64_t stream_begin, uint64_t stream_count,
                        cudaStream_t st, Plan* p) {
+  const int rc = plan_fill(r, stream_begin, stream_count, st, p);
+  if (rc) plan_destroy(p, st);
+  return rc;
+}
+static int plan_fill(const hexo_price_request* r, uint64_t stream_begin, uint64_t stream_count,
+                     cudaStream_t st, Plan* p) {
   int rc = check_request(r, true);
   if (rc) return rc;
   rc = ensure_context();
@@ -735,10 +744,16 @@ int hexo_gpu_price_shard(const hexo_price_request* req, uint64_t stream_begin,
   Plan p;
   int rc = plan_create(req, stream_begin, stream_count, st, &p);
   if (rc) return rc;
-  cudaEvent_t e0, e1;
-  HEXO_CUDA(cudaEventCreate(&e0));
-  HEXO_CUDA(cudaEventCreate(&e1));
-  HEXO_CUDA(cudaEventRecord(e0, st));
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  cudaError_t ee = cudaEventCreate(&e0);
+  if (ee == cudaSuccess) ee = cudaEventCreate(&e1);
+  if (ee == cudaSuccess) ee = cudaEventRecord(e0, st);
+  if (ee != cudaSuccess) {
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    plan_destroy(&p, st);
+    return fail(HEXO_ERR_CUDA, "timing events: %s", cudaGetErrorString(ee));
+  }
   rc = plan_launch(&p, st, nullptr);
   if (rc == HEXO_OK) {
     cudaEventRecord(e1, st);
