@@ -168,6 +168,9 @@ def run_ours(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # NCCL writes its version / debug lines to stdout by default: keep stdout to the one
+        # JSON line of the contract
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
     _lib.check(lib.hexo_gpu_init(local_rank))

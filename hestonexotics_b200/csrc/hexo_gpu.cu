@@ -79,11 +79,22 @@ static int ensure_context() {
                 e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
   int dev = 0;
   HEXO_CUDA(cudaGetDevice(&dev));
-  cudaDeviceProp prop;
-  HEXO_CUDA(cudaGetDeviceProperties(&prop, dev));
+  // single attributes, not cudaGetDeviceProperties: that call gathers every property of the
+  // device and was measured at 10-380 ms per call while other processes keep their GPUs busy
+  int sms = 0, smem = 0;
+  HEXO_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  HEXO_CUDA(cudaDeviceGetAttribute(&smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  // keep freed blocks of the stream-ordered allocator in the pool: a pricing call allocates and
+  // frees one small block, and returning it to the driver at every synchronisation makes the
+  // next call pay a real allocation (slow once peer access is enabled, as it is under NCCL)
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+    uint64_t keep = UINT64_MAX;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+  }
   g_ctx.device = dev;
-  g_ctx.sm_count = prop.multiProcessorCount;
-  g_ctx.smem_optin = prop.sharedMemPerBlockOptin;
+  g_ctx.sm_count = sms;
+  g_ctx.smem_optin = (size_t)smem;
   g_ctx.ready = true;
   return HEXO_OK;
 }
@@ -654,6 +665,9 @@ int hexo_gpu_init(int device) {
   if (n == 0) return fail(HEXO_ERR_NO_DEVICE, "no CUDA device visible");
   if (device < 0 || device >= n)
     return fail(HEXO_ERR_INVALID_ARGUMENT, "device %d out of range [0,%d)", device, n);
+  int cur = -1;
+  if (g_ctx.ready && g_ctx.device == device && cudaGetDevice(&cur) == cudaSuccess && cur == device)
+    return HEXO_OK;  // already set up for this device: callers may init before every call
   HEXO_CUDA(cudaSetDevice(device));
   g_ctx.ready = false;
   return ensure_context();
