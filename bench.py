@@ -169,7 +169,9 @@ def run_ours(args):
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         # NCCL writes its version / debug lines to stdout by default: keep stdout to the one
-        # JSON line of the contract
+        # JSON line of the contract.  NCCL_DEBUG_FILE is only honoured above the VERSION level.
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()

@@ -6,7 +6,7 @@ import hestonexotics_b200 as hx
 from hestonexotics_b200 import _lib
 rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(lr)
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+os.environ["NCCL_DEBUG"] = "WARN"; os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
 lib = _lib.load(); _lib.check(lib.hexo_gpu_init(lr))
 A = hx.HQEAnderson(hx.AAsianCallNonAdaptive); p = hx.HParams(0.04, 0.04, -0.7, 2.0, 0.5)
