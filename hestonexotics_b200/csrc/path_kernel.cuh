@@ -440,7 +440,7 @@ heston_qe_paths_kernel(const __grid_constant__ PathArgs a) {
   // pays four moves to line the words up in an aligned register quad) and a warp's 64-bit
   // accesses touch consecutive 8-byte slots
   const uint32_t zstride = pin32(Ring::kBytesPerStep * T), ustride = pin32(8 * T);
-  const uint32_t uplane = pin32(8 * kRing * T);
+  const uint32_t uplane = kRing * ustride;  // = 8 kRing T
   const uint32_t ucol = pin32(smem_addr(sp) + 8 * tid);  // variance word of step 0
   sp += (size_t)16 * kRing * T;
   const uint32_t zcol = pin32(smem_addr(sp) + Ring::kBytesPerStep * tid);
@@ -573,21 +573,25 @@ heston_qe_paths_kernel(const __grid_constant__ PathArgs a) {
             }
             uint32_t m = min(kRing - pos, count);
             count -= m;
-            uint32_t za = zcol + pos * zstride, ua = ucol + pos * ustride;
+            uint32_t za = zcol + pos * zstride;
+            // the variance word of the step whose normals sit at `z` (read on the psi >= 1.5
+            // path only: derived there instead of carried through the loop)
+            auto uniform_at = [&](uint32_t z) {
+              return u64_to_unit(lds_b64(ucol + (z - zcol) / (Ring::kBytesPerStep / 8)));
+            };
             pos += m;
             if (first) {  // prologue: variance half of the first step
               first = false;
               double zv;
               Ring::get(za, zv, zx_pend);
               Vold = V;
-              V = qe_variance<MART>(g, Vold, zv, [ua]() { return u64_to_unit(lds_b64(ua)); },
-                                    &k0_pend);
-              --m, za += zstride, ua += ustride;
+              V = qe_variance<MART>(g, Vold, zv, [&]() { return uniform_at(za); }, &k0_pend);
+              --m, za += zstride;
             }
             // unrolled by two so that the loop-carried rotation (Vold <- V <- V', Z_X) becomes
             // register renaming instead of moves
 #pragma unroll 2
-            for (; m; --m, za += zstride, ua += ustride) {
+            for (; m; --m, za += zstride) {
               double zv, zx;
               Ring::get(za, zv, zx);
               // Second half of the previous step and first half of this one, straight-line
@@ -605,8 +609,7 @@ heston_qe_paths_kernel(const __grid_constant__ PathArgs a) {
                 if (rare_x | mid.rare) {
                   if (rare_x) Xn = grow_spot_rare(X, delta, exptab_s);
                   if (mid.rare)
-                    Vn = qe_variance_rare<MART>(g, V, mid,
-                                                [ua]() { return u64_to_unit(lds_b64(ua)); });
+                    Vn = qe_variance_rare<MART>(g, V, mid, [&]() { return uniform_at(za); });
                 }
                 X = Xn;
                 sumX += X;
@@ -617,8 +620,7 @@ heston_qe_paths_kernel(const __grid_constant__ PathArgs a) {
                   X = fast_exp(lnX, exptab_s);
                 }
                 if (mid.rare)
-                  Vn = qe_variance_rare<MART>(g, V, mid,
-                                              [ua]() { return u64_to_unit(lds_b64(ua)); });
+                  Vn = qe_variance_rare<MART>(g, V, mid, [&]() { return uniform_at(za); });
               }
               Vold = V;
               V = Vn;
