@@ -298,9 +298,9 @@ def run_ours(args):
                 "unit": "TFLOP/s", "frac": achieved / fl.value,
                 # dram__bytes_read.sum + dram__bytes_write.sum of the path kernel in the round-1
                 # `ncu --set full` capture (profiles/r01_path_kernel_ncu_raw_final.csv, a
-                # 4.1e9-path-step launch): 469 248 B read, 0 B written -- code and constants only
+                # 4.1e9-path-step launch): 85 248 B read, 0 B written -- code and constants only
                 # (61 KB ... 469 KB from capture to capture), it does not grow with the paths
-                "traffic": 469248,
+                "traffic": 85248,
                 "note": "achieved = 100 algorithmic FP64 flop per path-step (SURVEY 8d) x path-steps "
                         "of one GPU / mean path-kernel time (CUDA events); peak = DFMA peak measured "
                         "in this run (hexo_gpu_measure_fp64_peak; MEASURED_PEAKS.json has no FP64 "

@@ -608,7 +608,7 @@ heston_qe_paths_kernel(const __grid_constant__ PathArgs a) {
                 const bool rare_x = grow_spot_is_rare(delta);
                 if (rare_x | mid.rare) {
                   if (rare_x) Xn = grow_spot_rare(X, delta, exptab_s);
-                  if (mid.rare)
+                  if (qe_rare_again(mid))
                     Vn = qe_variance_rare<MART>(g, V, mid, [&]() { return uniform_at(za); });
                 }
                 X = Xn;

@@ -57,6 +57,7 @@ struct SegConst {
 struct QeVarMid {
   double m, s2h;  // :59, :60 (s^2/2)
   bool rare;      // psi >= 1.5: the quadratic value has to be replaced by qe_variance_rare
+  int t_hi;       // high word of 3 w - s^2/2, what `rare` was read from (rare_again())
   double k0;      // MART only: K0* + (K1 + K3/2) V = -ln M of this step
 };
 
@@ -76,7 +77,8 @@ __device__ __forceinline__ double qe_variance_quad(const SegConst& g, const doub
   // :63  psi >= 1.5  <=>  3 w <= s^2/2.  Read off the sign of 3 w - s^2/2 on the integer pipe
   // (the high word; a positive denormal counts as zero, where both branches are valid) instead of
   // a multiply and a compare on the FP64 pipe.
-  mid.rare = __double2hiint(fma(3.0, w, -s2h)) <= 0;
+  mid.t_hi = __double2hiint(fma(3.0, w, -s2h));
+  mid.rare = mid.t_hi <= 0;
   if (MART) {
     const double d = fma(-g.A2, dm, 1.0);                   // 1 - 2 A a
     const double k0 = fma(0.5, fast_log(d), -(g.A * sw) * fast_rcp(d));
@@ -84,6 +86,15 @@ __device__ __forceinline__ double qe_variance_quad(const SegConst& g, const doub
     mid.k0 = d > 0.0 ? k0 : fma(g.K1 - g.K1m, V, g.K0);
   }
   return fma(zv, fma(dm, zv, me + me), sw);                 // :64-68
+}
+
+// `mid.rare` once more, for code that already sits behind a branch on it together with other
+// conditions: recomputed from the integer there, so that the hot path does not keep a second
+// predicate alive for it (ptxas otherwise issues the compare twice per step)
+__device__ __forceinline__ bool qe_rare_again(const QeVarMid& mid) {
+  int t = mid.t_hi;
+  asm volatile("" : "+r"(t));
+  return t <= 0;
 }
 
 // Exponential / zero-mass branch (:70-73), a few per cent of the warp-steps, straight-line
