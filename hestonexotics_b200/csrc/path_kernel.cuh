@@ -9,9 +9,10 @@
 //  * one thread = one independent shishua stream (seed {seed, stream, 0, 0});
 //    RNG state, variance, log-spot and the running integral stay in registers;
 //    no path data touches HBM;
-//  * every 8 steps a thread advances its generator one round (16 words), turns
-//    them into 8 (Z_V, Z_X) pairs in one batch (normals.cuh) and parks them in
-//    its own column of shared memory; the step loop reads one pair per step;
+//  * every ring_steps() steps (16 with F32 normals, 8 with F64) a thread advances its
+//    generator (one round = 16 words = 8 steps), turns the words into (Z_V, Z_X) pairs
+//    in one batch (normals.cuh) and parks them in its own column of shared memory; the
+//    step loop reads one pair per step;
 //  * when a maturity is reached the 32 final values of a warp are exchanged
 //    through shared memory and each lane owns a strided subset of the strikes,
 //    so per-option sums are accumulated without atomics and in a fixed order;
@@ -75,7 +76,7 @@ struct PathArgs {
 //                 words first, then spot words.  Kept because the tail phase of
 //                 the normal transform re-reads them and because the psi >= 1.5
 //                 branch needs the UNIFORM of the variance draw (HSimulation.tpp:72)
-//   zring  [8][T] pairs (Z_V, Z_X) of the round, float2 (F32 mode) / double2 (F64)
+//   zring  [R][T] pairs (Z_V, Z_X) of the refill, float2 (F32 mode) / double2 (F64)
 //   exptab [32]   2^(j/32)
 //   fvbuf  [W][32] final values of a warp at a maturity
 //   acc    [W][n_acc] lane-owned payoff sums / sums of squares (/ control-variate sums)
