@@ -23,6 +23,7 @@ ABI_SYMBOLS = (
     "hexo_gpu_plan_sums_device", "hexo_gpu_plan_stats", "hexo_gpu_plan_destroy",
     "hexo_gpu_philox4x32", "hexo_gpu_philox_streams", "hexo_gpu_price_batch",
     "hexo_gpu_schedule_exact", "hexo_gpu_sums_len", "hexo_gpu_finish",
+    "hexo_gpu_normals_from_words",
 )
 # host-only semi-analytic benchmark functions of the same library (no hexo_gpu_ prefix)
 HOST_SYMBOLS = ("hexo_heston_chf", "hexo_swift_default_params", "hexo_swift_price_chain")
@@ -128,7 +129,8 @@ def load() -> C.CDLL:
     lib.hexo_gpu_u64_to_unit.argtypes = [c_uint64_p, c_double_p, C.c_size_t]
     lib.hexo_gpu_ppnd16.argtypes = [c_double_p, c_double_p, C.c_size_t, C.c_int]
     lib.hexo_gpu_replay.argtypes = [C.POINTER(HexoPriceRequest), c_double_p, C.c_uint64,
-                                    C.c_uint32, c_double_p]
+                                    C.c_uint32, c_double_p, c_uint32_p]
+    lib.hexo_gpu_normals_from_words.argtypes = [c_uint64_p, c_double_p, C.c_size_t, C.c_int]
     lib.hexo_gpu_measure_fp64_peak.argtypes = [c_double_p, C.POINTER(C.c_float)]
     lib.hexo_heston_chf.argtypes = [C.POINTER(HexoHParams), C.c_double, C.c_double, C.c_double,
                                     c_double_p]
@@ -138,7 +140,7 @@ def load() -> C.CDLL:
     lib.hexo_swift_price_chain.argtypes = [C.POINTER(HexoSwiftParams), C.POINTER(HexoHParams),
                                            C.c_double, C.c_double, C.c_double, c_double_p,
                                            C.c_uint32, c_double_p, c_double_p]
-    if lib.hexo_gpu_abi_version() != 3:
+    if lib.hexo_gpu_abi_version() != 4:
         raise ImportError("libhexo_gpu.so has an unexpected ABI version; rebuild it")
     _lib = lib
     return lib

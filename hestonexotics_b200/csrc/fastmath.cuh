@@ -73,6 +73,18 @@ __device__ __forceinline__ double fast_sqrt(double a) {
   return fma(g, q * r, g);
 }
 
+// sign(a) sqrt(|a|): the same correction seeded from |a| -- the seed instruction only reads the
+// high word, so the absolute value is one integer AND, not an FP64 instruction.  For arguments
+// that are non-negative up to rounding: a slightly negative one gives a slightly negative
+// result instead of NaN.
+__device__ __forceinline__ double fast_sqrt_signed(double a) {
+  const double y0 = mufu_rsqrt64(__hiloint2double(__double2hiint(a) & 0x7fffffff, 0));
+  const double g = a * y0;
+  const double r = fma(-fabs(g), y0, 1.0);
+  const double q = fma(0.375, r, 0.5);
+  return fma(g, q * r, g);
+}
+
 // exp(x) for |x| < 700: x = (32 k + j) ln2/32 + r, exp(x) = 2^k 2^(j/32) e^r with
 // |r| <= ln2/64 and a degree-6 Taylor polynomial (remainder r^7/5040 < 4e-18).
 // `tab_saddr` is the shared-space byte address of the 32-entry table 2^(j/32)

@@ -60,7 +60,9 @@ static int fail(int code, const char* fmt, ...) {
   } while (0)
 
 // ---------------------------------------------------------------------------
-// device context (one process drives one GPU)
+// device contexts: one per visible GPU, set up on first use.  A process normally drives one
+// GPU (one rank per GPU); hexo_gpu_price_multi drives several from one process, and each of
+// them needs its own SM count, shared-memory limit and memory-pool setting.
 // ---------------------------------------------------------------------------
 struct Context {
   bool ready = false;
@@ -68,17 +70,26 @@ struct Context {
   int sm_count = 0;
   size_t smem_optin = 0;
 };
-static Context g_ctx;
+constexpr int kMaxDevices = 64;
+static Context g_ctxs[kMaxDevices];
+static thread_local Context* g_cur = nullptr;  // context of the calling thread's current device
+#define g_ctx (*g_cur)
 
+// points g_cur at the context of the current device, initialising it if need be
 static int ensure_context() {
-  if (g_ctx.ready) return HEXO_OK;
   int n = 0;
   cudaError_t e = cudaGetDeviceCount(&n);
-  if (e != cudaSuccess || n == 0)
+  if (e != cudaSuccess || n == 0) {
+    cudaGetLastError();
     return fail(HEXO_ERR_NO_DEVICE, "no CUDA device: %s",
                 e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+  }
   int dev = 0;
   HEXO_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= kMaxDevices)
+    return fail(HEXO_ERR_INVALID_ARGUMENT, "device %d: at most %d devices", dev, kMaxDevices);
+  g_cur = &g_ctxs[dev];
+  if (g_ctx.ready) return HEXO_OK;
   // single attributes, not cudaGetDeviceProperties: that call gathers every property of the
   // device and was measured at 10-380 ms per call while other processes keep their GPUs busy
   int sms = 0, smem = 0;
@@ -164,6 +175,47 @@ template <int NORMAL_MODE>
 __global__ void ppnd16_kernel(const double* in, double* out, size_t n) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = ppnd16<NORMAL_MODE>(in[i]);
+}
+
+// K3b: the normal transform EXACTLY as the path kernel runs it.  ppnd16_kernel above evaluates
+// the scalar AS241 routine; K1 does not call that one but ring_refill (path_kernel.cuh): batched
+// central phase (two draws per FFMA2, q from the high word), then the warp-cooperative tail
+// phase through the shared-memory ring.  This kernel feeds caller-supplied words through
+// ring_refill in place of generator rounds and reads the normals back from the z ring the way
+// the step loop does.  Thread c transforms words [c W, (c + 1) W), W = 2 ring_steps; word 2 s of
+// a chunk is the variance word of step s, word 2 s + 1 its spot word.
+struct WordSource {
+  const uint64_t* p;  // nullptr: central filler words (threads past the end of the input)
+  __device__ __forceinline__ void round(uint64_t (&o)[16]) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) o[j] = p ? p[j] : 0x8000000000000000ull;
+    if (p) p += 16;
+  }
+};
+template <int NORMAL_MODE>
+__global__ void __launch_bounds__(kMaxBlock)
+normals_from_words_kernel(const uint64_t* __restrict__ words, double* __restrict__ z,
+                          uint64_t n_chunks) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  using Ring = ZRing<NORMAL_MODE>;
+  constexpr int kRing = ring_steps(NORMAL_MODE), kWords = 2 * kRing;
+  const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t base = smem_addr(smem_raw);
+  const RingAddr ra = {base + 8 * tid, (uint32_t)(8 * T),
+                       base + 16 * kRing * T + Ring::kBytesPerStep * tid,
+                       (uint32_t)(Ring::kBytesPerStep * T),
+                       base + (16 + Ring::kBytesPerStep) * kRing * T + kTailListBytes * warp};
+  const uint64_t chunk = (uint64_t)blockIdx.x * T + tid;
+  WordSource src{chunk < n_chunks ? words + chunk * kWords : nullptr};
+  uint64_t o[16];
+  ring_refill<NORMAL_MODE>(src, o, false, ra, lane);
+  if (chunk >= n_chunks) return;
+  for (int s = 0; s < kRing; ++s) {
+    double zv, zx;
+    Ring::get(ra.zcol + s * ra.zstride, zv, zx);
+    z[chunk * kWords + 2 * s] = zv;
+    z[chunk * kWords + 2 * s + 1] = zx;
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -396,12 +448,41 @@ static size_t sums_len(const hexo_price_request* r) {
   return r->control_variate ? 3 * n_opts + 2 * (size_t)r->n_chains : 2 * n_opts;
 }
 
+// Known mean of the control c = final value - S of every maturity.  The spot is a martingale
+// (r = 0; exactly under HEXO_DRIFT_MARTINGALE, up to the QE drift error otherwise), so
+// E[X_j] = S on every grid point and E[final value] = S x (sum of the weights the policy
+// actually applies) / T.  European: the interpolated X_T, weights sum to 1, E[c] = 0.  Asian:
+// the trapezoid weights of the schedule.  On the reference grid they do NOT sum to T when the
+// steps land exactly on the expiry (SURVEY finding 6: the last trapezoid is replaced by
+// (X_N - X_{N-1}) w, mean zero), e.g. E[average] = S (1 - 1/steps) for a power-of-two step count.
+static void control_means(const hexo_price_request* r, const std::vector<SegConst>& segs,
+                          std::vector<double>& ec) {
+  ec.assign(r->n_chains, 0.0);
+  if (r->payoff != HEXO_PAYOFF_ASIAN) return;
+  double weight = 0.0;  // sum of trapezoid weights accumulated in `integral` (path kernel)
+  for (uint32_t k = 0; k < r->n_chains; ++k) {
+    const SegConst& g = segs[k];
+    if (g.n_steps > 0) {
+      if (k > 0) weight += 2.0 * g.hcarry;      // trapezoid of the step that crossed expiry k-1
+      weight += g.h * (double)(g.n_steps - 1);  // all but the crossing step of this segment
+    }
+    ec[k] = r->S * ((weight + 2.0 * g.hs) / g.expiry - 1.0);  // dx * w has mean zero
+  }
+}
+
 // sums -> prices and standard errors.  Plain: mean payoff (HSimulation.tpp:40 divides by
-// n_simulations) and its standard error.  Control variate: c = final value - S has mean 0 (the
-// spot is a martingale, r = 0), so  price = mean(pf) - beta mean(c),  beta = cov(pf, c)/var(c),
-// and the variance shrinks by 1 - corr(pf, c)^2.
-static void finish_prices(const hexo_price_request* r, const double* sums, double* prices,
-                          double* se) {
+// n_simulations) and its standard error.  Control variate: c = final value - S with the known
+// mean E[c] of control_means, so  price = mean(pf) - beta (mean(c) - E[c]),
+// beta = cov(pf, c)/var(c), and the variance shrinks by 1 - corr(pf, c)^2.
+static int finish_prices(const hexo_price_request* r, const double* sums, double* prices,
+                         double* se) {
+  std::vector<double> ec(r->n_chains, 0.0);
+  if (r->control_variate) {
+    std::vector<SegConst> segs;
+    const int rc = build_segments(r, true, segs, nullptr);
+    if (rc) return rc;
+    control_means(r, segs, ec);
+  }
   const uint32_t n_opts = r->strike_offsets[r->n_chains];
   const double n = (double)r->n_paths;
   const double* sp = sums;
@@ -422,13 +503,14 @@ static void finish_prices(const hexo_price_request* r, const double* sums, doubl
       if (r->control_variate && var_c > 0.0) {
         const double cov = (sx[j] - n * mean * mean_c) / (n - 1);
         const double beta = cov / var_c;
-        price = mean - beta * mean_c;
+        price = mean - beta * (mean_c - ec[k]);
         var = std::max(0.0, var - beta * cov);
       }
       prices[j] = price;
       if (se) se[j] = sqrt(var / n);
     }
   }
+  return HEXO_OK;
 }
 
 // ---------------------------------------------------------------------------
@@ -444,8 +526,6 @@ struct Plan {
   size_t gacc_bytes = 0;
   bool cv = false;  // control-variate sums (template parameter CV of the path kernel)
   bool mart = false;  // HEXO_DRIFT_MARTINGALE (template parameter MART)
-  bool ws = false;  // warp-specialised kernel (path_kernel_ws.cuh)
-  bool il = false;  // interleaved look-ahead kernel (path_kernel_il.cuh)
 };
 
 // The path-kernel instantiations live in their own translation units (path_kernels_*.cu), which
@@ -462,25 +542,11 @@ static PathKernel pick_kernel(int payoff, int normal_mode, uint32_t n_seg, int r
   return cv ? path_kernel_shishua_cv(payoff, normal_mode, segs)
             : path_kernel_shishua(payoff, normal_mode, segs);
 }
-static PathKernelWs pick_ws_kernel(int payoff, int normal_mode, uint32_t n_seg) {
-  return path_kernel_ws(payoff, normal_mode, n_seg <= (uint32_t)kInlineSegs);
-}
-static PathKernel pick_il_kernel(int payoff, int normal_mode, uint32_t n_seg) {
-  return path_kernel_il(payoff, normal_mode, n_seg <= (uint32_t)kInlineSegs);
-}
-static bool use_il() {
-  const char* e = getenv("HEXO_IL");
-  return e && atoi(e) != 0;
-}
-static bool use_ws() {
-  const char* e = getenv("HEXO_WS");
-  return e && atoi(e) != 0;
-}
 
 static uint64_t default_streams(uint64_t n_paths, int n_gpus) {
   // one wave of resident threads per GPU
-  const uint64_t per_gpu = (uint64_t)(g_ctx.ready ? g_ctx.sm_count : 148) *
-                           (use_ws() ? kWsMinBlocks * kWsConsumers : kMinBlocksPerSM * kMaxBlock);
+  const uint64_t per_gpu = (uint64_t)(g_cur && g_ctx.ready ? g_ctx.sm_count : 148) *
+                           (uint64_t)(kMinBlocksPerSM * kMaxBlock);
   uint64_t s = per_gpu * (uint64_t)std::max(n_gpus, 1);
   if (s > n_paths) s = n_paths;
   return std::max<uint64_t>(s, 1);
@@ -519,26 +585,19 @@ static int plan_fill(const hexo_price_request* r, uint64_t stream_begin, uint64_
   // Per-warp option accumulators live in shared memory while that leaves room for
   // kMinBlocksPerSM blocks per SM; larger chains accumulate in (L2-resident) device memory.
   int block = kMaxBlock;
-  if (const char* e = getenv("HEXO_BLOCK")) {  // development knob: 32..256, multiple of 32
+#ifdef HEXO_DEV_PROBES  // development builds only (build.py --dev): never in the shipped library
+  if (const char* e = getenv("HEXO_BLOCK")) {  // 32..256, multiple of 32
     const int b = atoi(e);
     if (b >= 32 && b <= kMaxBlock && b % 32 == 0) block = b;
   }
+#endif
   p->rng_mode = r->rng_mode;
-  const bool plain = r->rng_mode == HEXO_RNG_SHISHUA && !r->control_variate &&
-                     r->drift_mode == HEXO_DRIFT_REFERENCE;
   const uint32_t n_sums = (uint32_t)sums_len(r);
   p->n_sums = n_sums;
-  p->ws = plain && use_ws();  // the WS / IL experiments carry neither Philox nor the control variate
-  const size_t smem_budget = std::min(
-      g_ctx.smem_optin, (size_t)(227 * 1024) / (p->ws ? kWsMinBlocks : kMinBlocksPerSM));
-  if (p->ws) block = kWsBlock;
-  p->il = plain && !p->ws && use_il();
-  const int streams_per_block = p->ws ? kWsConsumers : block;  // path-owning threads per block
-  auto smem_of = [&](bool acc) {
-    return p->ws   ? path_kernel_ws_smem(n_opts, r->normal_mode, acc)
-           : p->il ? path_kernel_il_smem(block, n_opts, r->normal_mode, acc)
-                   : path_kernel_smem(block, n_sums, r->normal_mode, acc);
-  };
+  const size_t smem_budget =
+      std::min(g_ctx.smem_optin, (size_t)(227 * 1024) / kMinBlocksPerSM);
+  const int streams_per_block = block;  // path-owning threads per block
+  auto smem_of = [&](bool acc) { return path_kernel_smem(block, n_sums, r->normal_mode, acc); };
   const bool acc_in_smem = smem_of(true) <= smem_budget;
   p->payoff = r->payoff;
   p->normal_mode = r->normal_mode;
@@ -587,37 +646,32 @@ static int plan_fill(const hexo_price_request* r, uint64_t stream_begin, uint64_
   for (size_t k = 0; k < segs.size() && k < (size_t)kInlineSegs; ++k) a.seg_inline[k] = segs[k];
   a.strikes = reinterpret_cast<const double*>(base + off_strikes);
   a.partials = reinterpret_cast<double*>(base + off_part);
+#ifdef HEXO_DEV_PROBES
   {
     const char* e = getenv("HEXO_NO_REFILL");
     a.dev_no_refill = (e && atoi(e) != 0) ? 1u : 0u;
   }
+#endif
   a.gacc = acc_in_smem ? nullptr : reinterpret_cast<double*>(base + off_gacc);
   p->gacc_bytes = gacc_bytes;
 
-  if (p->ws) {
-    PathKernelWs kern = pick_ws_kernel(p->payoff, p->normal_mode, p->args.n_seg);
-    HEXO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem));
-  } else {
-    PathKernel kern = p->il ? pick_il_kernel(p->payoff, p->normal_mode, p->args.n_seg)
-                            : pick_kernel(p->payoff, p->normal_mode, p->args.n_seg, p->rng_mode,
-                                           p->cv, p->mart);
-    HEXO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->smem));
-  }
+  // The attribute belongs to the kernel function, not to the plan, and a later, smaller value
+  // would overwrite it: always ask for the device maximum, so that plans with different option
+  // counts (and host threads) can coexist.  It is a cap; occupancy follows the size actually
+  // passed at launch.
+  PathKernel kern = pick_kernel(p->payoff, p->normal_mode, p->args.n_seg, p->rng_mode, p->cv,
+                                p->mart);
+  HEXO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)g_ctx.smem_optin));
   return HEXO_OK;
 }
 
 // enqueue path kernel + reduction; sums land in `sums_out_dev` (or the plan's own buffer)
 static int plan_launch(const Plan* p, cudaStream_t st, double* sums_out_dev) {
   if (p->args.gacc) HEXO_CUDA(cudaMemsetAsync(p->args.gacc, 0, p->gacc_bytes, st));
-  if (p->ws) {
-    PathKernelWs kern = pick_ws_kernel(p->payoff, p->normal_mode, p->args.n_seg);
-    kern<<<p->grid, p->block, p->smem, st>>>(p->args, (uint32_t)p->steps_per_path);
-  } else {
-    PathKernel kern = p->il ? pick_il_kernel(p->payoff, p->normal_mode, p->args.n_seg)
-                            : pick_kernel(p->payoff, p->normal_mode, p->args.n_seg, p->rng_mode,
-                                           p->cv, p->mart);
-    kern<<<p->grid, p->block, p->smem, st>>>(p->args);
-  }
+  PathKernel kern = pick_kernel(p->payoff, p->normal_mode, p->args.n_seg, p->rng_mode, p->cv,
+                                p->mart);
+  kern<<<p->grid, p->block, p->smem, st>>>(p->args);
   HEXO_CUDA(cudaGetLastError());
   const uint32_t n2 = p->n_sums;
   reduce_partials_kernel<<<(n2 + 127) / 128, 128, 0, st>>>(p->args.partials, p->grid, n2,
@@ -666,15 +720,13 @@ int hexo_gpu_init(int device) {
   if (device < 0 || device >= n)
     return fail(HEXO_ERR_INVALID_ARGUMENT, "device %d out of range [0,%d)", device, n);
   int cur = -1;
-  if (g_ctx.ready && g_ctx.device == device && cudaGetDevice(&cur) == cudaSuccess && cur == device)
-    return HEXO_OK;  // already set up for this device: callers may init before every call
-  HEXO_CUDA(cudaSetDevice(device));
-  g_ctx.ready = false;
-  return ensure_context();
+  if (cudaGetDevice(&cur) != cudaSuccess || cur != device) HEXO_CUDA(cudaSetDevice(device));
+  return ensure_context();  // cheap when the device is already set up: callers may init per call
 }
 
 int hexo_gpu_shutdown(void) {
-  g_ctx.ready = false;
+  for (int d = 0; d < kMaxDevices; ++d) g_ctxs[d].ready = false;
+  g_cur = nullptr;
   return HEXO_OK;
 }
 
@@ -797,8 +849,7 @@ int hexo_gpu_price(const hexo_price_request* req, double* prices_out, double* st
   std::vector<double> sums(sums_len(&r));
   rc = hexo_gpu_price_shard(&r, 0, r.n_streams, sums.data(), stats);
   if (rc) return rc;
-  finish_prices(&r, sums.data(), prices_out, stderr_out);
-  return HEXO_OK;
+  return finish_prices(&r, sums.data(), prices_out, stderr_out);
 }
 
 size_t hexo_gpu_sums_len(const hexo_price_request* req) {
@@ -811,8 +862,7 @@ int hexo_gpu_finish(const hexo_price_request* req, const double* sums, double* p
   int rc = check_request(req, true);
   if (rc) return rc;
   if (!sums || !prices_out) return fail(HEXO_ERR_INVALID_ARGUMENT, "finish: sums / prices_out is NULL");
-  finish_prices(req, sums, prices_out, stderr_out);
-  return HEXO_OK;
+  return finish_prices(req, sums, prices_out, stderr_out);
 }
 
 // Many independent price<>() calls in one submission (Monte-Carlo inside a
@@ -887,8 +937,9 @@ int hexo_gpu_price_batch(const hexo_price_request* reqs, uint32_t n_reqs, uint32
   if (e != cudaSuccess) return fail(HEXO_ERR_CUDA, "batch: %s", cudaGetErrorString(e));
   size_t out_off = 0;
   for (uint32_t i = 0; i < n_reqs; ++i) {
-    finish_prices(&reqs[i], sums.data() + off[i], prices_out + out_off,
-                  stderr_out ? stderr_out + out_off : nullptr);
+    rc = finish_prices(&reqs[i], sums.data() + off[i], prices_out + out_off,
+                       stderr_out ? stderr_out + out_off : nullptr);
+    if (rc) return rc;
     out_off += reqs[i].strike_offsets[reqs[i].n_chains];
     if (stats) fill_stats(plans[i], ms, &stats[i]);  // kernel_ms = the whole batch
   }
@@ -915,7 +966,6 @@ int hexo_gpu_price_multi(const hexo_price_request* req, int n_gpus, double* pric
   if (rc) return rc;
   hexo_price_request r = *req;
   if (r.n_streams == 0) r.n_streams = default_streams(r.n_paths, n_gpus);
-  const uint32_t n_opts = r.strike_offsets[r.n_chains];
   std::vector<Plan> plans(n_gpus);
   std::vector<int> used(n_gpus, 0);
   std::vector<cudaEvent_t> ev0(n_gpus), ev1(n_gpus);
@@ -961,8 +1011,7 @@ int hexo_gpu_price_multi(const hexo_price_request* req, int n_gpus, double* pric
   if (rc) return rc;
   fill_stats(plans[0], ms_max, stats);
   if (stats) stats->kernel_launches = 2 * (uint32_t)n_gpus;
-  finish_prices(&r, sums.data(), prices_out, stderr_out);
-  return HEXO_OK;
+  return finish_prices(&r, sums.data(), prices_out, stderr_out);
 }
 
 int hexo_gpu_shishua_streams(uint64_t seed, uint64_t first_stream, uint32_t n_streams,
@@ -1082,8 +1131,49 @@ int hexo_gpu_ppnd16(const double* u_in, double* z_out, size_t n, int normal_mode
   return HEXO_OK;
 }
 
+int hexo_gpu_normals_from_words(const uint64_t* words_in, double* z_out, size_t n, int normal_mode) {
+  if (!words_in || !z_out || n == 0)
+    return fail(HEXO_ERR_INVALID_ARGUMENT, "normals_from_words: bad args");
+  if (normal_mode != HEXO_NORMAL_F32 && normal_mode != HEXO_NORMAL_F64)
+    return fail(HEXO_ERR_INVALID_ARGUMENT, "unknown normal_mode %d", normal_mode);
+  int rc = ensure_context();
+  if (rc) return rc;
+  const size_t kw = 2 * (size_t)ring_steps(normal_mode);
+  const size_t n_chunks = (n + kw - 1) / kw, padded = n_chunks * kw;
+  const int block = kMaxBlock;
+  const size_t smem = (size_t)(16 + (normal_mode == HEXO_NORMAL_F64 ? 16 : 8)) *
+                          ring_steps(normal_mode) * block + (size_t)kTailListBytes * (block / 32);
+  uint64_t* dw = nullptr;
+  double* dz = nullptr;
+  HEXO_CUDA(cudaMalloc(&dw, padded * 8));
+  HEXO_CUDA(cudaMalloc(&dz, padded * 8));
+  // pad the last chunk with central words (p = 1/2)
+  std::vector<uint64_t> pad(padded - n, 0x8000000000000000ull);
+  cudaError_t e = cudaMemcpy(dw, words_in, n * 8, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess && !pad.empty())
+    e = cudaMemcpy(dw + n, pad.data(), pad.size() * 8, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    const unsigned grid = (unsigned)((n_chunks + block - 1) / block);
+    if (normal_mode == HEXO_NORMAL_F64) {
+      e = cudaFuncSetAttribute(normals_from_words_kernel<1>,
+                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_ctx.smem_optin);
+      if (e == cudaSuccess) normals_from_words_kernel<1><<<grid, block, smem>>>(dw, dz, n_chunks);
+    } else {
+      e = cudaFuncSetAttribute(normals_from_words_kernel<0>,
+                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_ctx.smem_optin);
+      if (e == cudaSuccess) normals_from_words_kernel<0><<<grid, block, smem>>>(dw, dz, n_chunks);
+    }
+    if (e == cudaSuccess) e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpy(z_out, dz, n * 8, cudaMemcpyDeviceToHost);
+  cudaFree(dw);
+  cudaFree(dz);
+  if (e != cudaSuccess) return fail(HEXO_ERR_CUDA, "normals_from_words: %s", cudaGetErrorString(e));
+  return HEXO_OK;
+}
+
 int hexo_gpu_replay(const hexo_price_request* req, const double* tape, uint64_t n_paths,
-                    uint32_t tape_steps, double* finals_out) {
+                    uint32_t tape_steps, double* finals_out, uint32_t* steps_used_out) {
   int rc = check_request(req, false);
   if (rc) return rc;
   if (!tape || !finals_out || n_paths == 0)
@@ -1123,7 +1213,8 @@ int hexo_gpu_replay(const hexo_price_request* req, const double* tape, uint64_t 
   cudaFree(dtape);
   cudaFree(dfin);
   if (e != cudaSuccess) return fail(HEXO_ERR_CUDA, "replay: %s", cudaGetErrorString(e));
-  return (int)steps_per_path;
+  if (steps_used_out) *steps_used_out = (uint32_t)steps_per_path;
+  return HEXO_OK;
 }
 
 int hexo_gpu_measure_fp64_peak(double* flops_out, float* ms_out) {

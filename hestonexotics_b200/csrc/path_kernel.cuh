@@ -46,6 +46,15 @@ __host__ __device__ constexpr int ring_steps(int normal_mode) {
   return normal_mode == HEXO_NORMAL_F64 ? kStepsPerRound : 2 * kStepsPerRound;
 }
 constexpr int kInlineSegs = 8;     // maturities whose constants travel as kernel parameters
+// Entries of a warp's tail list (16 bits each).  A refill of 16 steps has 32 x 32 draws per
+// warp, 15 % of them tails: 154 +- 11.  A refill with more tail draws than the list holds takes
+// the per-lane loop instead.
+constexpr int kTailListCap = 256;
+constexpr int kTailListBytes = 2 * kTailListCap;
+#ifndef HEXO_TAIL_COOP
+#define HEXO_TAIL_COOP 1  // 0: every lane loops over its own tail draws (the round-1 scheme)
+#endif
+
 
 struct PathArgs {
   double v0, S, lnS;
@@ -64,8 +73,10 @@ struct PathArgs {
   // mean: the spot is a martingale, r = 0) adds [sum pf c] per option and [sum c | sum c^2] per
   // maturity: 3 n_opts + 2 n_seg.
   double* partials;  // [gridDim.x][n_acc]
-  uint32_t dev_no_refill;  // development probe (HEXO_NO_REFILL=1): reuse the first generator
-                           // round forever, i.e. time the FP64 step loop alone
+#ifdef HEXO_DEV_PROBES
+  uint32_t dev_no_refill;  // development build only (HEXO_NO_REFILL=1): reuse the first refill
+                           // forever, i.e. time the FP64 step loop alone (wrong prices!)
+#endif
   double* gacc;      // nullptr: per-warp accumulators in shared memory; else zero-initialised
                      // [gridDim.x][warps][n_acc] in device memory (large option chains,
                      // where shared-memory accumulators would cost occupancy)
@@ -79,6 +90,7 @@ struct PathArgs {
 //   zring  [R][T] pairs (Z_V, Z_X) of the refill, float2 (F32 mode) / double2 (F64)
 //   exptab [32]   2^(j/32)
 //   fvbuf  [W][32] final values of a warp at a maturity
+//   tlist  [W][kTailListCap] 16-bit entries: the warp's tail draws of a refill (tail_phase_coop)
 //   acc    [W][n_acc] lane-owned payoff sums / sums of squares (/ control-variate sums)
 __host__ __device__ inline size_t path_kernel_smem(int block, uint32_t n_acc, int normal_mode,
                                                    bool acc_in_smem = true) {
@@ -86,7 +98,7 @@ __host__ __device__ inline size_t path_kernel_smem(int block, uint32_t n_acc, in
   const size_t steps = ring_steps(normal_mode);
   const size_t zbytes = (normal_mode == HEXO_NORMAL_F64 ? 16 : 8) * steps * block;
   return zbytes + (size_t)16 * steps * block + 32 * 8 + (size_t)32 * 8 * warps +
-         (acc_in_smem ? (size_t)warps * n_acc * 8 : 0);
+         (size_t)kTailListBytes * warps + (acc_in_smem ? (size_t)warps * n_acc * 8 : 0);
 }
 
 // ---- shared-space accessors (32-bit addresses: no generic-pointer arithmetic
@@ -144,84 +156,36 @@ __device__ __forceinline__ uint32_t bfind32(uint32_t x) {
   return r;
 }
 
-// Raw words -> normals for one generator round, in two phases (normals.cuh):
-// central formula for all 16 draws, then a per-lane loop over this lane's tail draws.
-//   wcol / zcol : shared addresses of this thread's step-0 slots, wstride / zstride
-//                 the distance between consecutive steps
+__device__ __forceinline__ void sts_u16(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((unsigned short)v));
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+
+// Shared-memory ring of one thread (addresses in the shared window).  Raw words live in two
+// planes [variance words | spot words] of RING steps each, so word j of a refill (j = RING d +
+// step, d = 0 variance / 1 spot) sits at ucol + j ustride; the (Z_V, Z_X) pair of step s sits at
+// zcol + s zstride.  Lane l of a warp owns column l: ucol = (lane 0's ucol) + 8 l.
+struct RingAddr {
+  uint32_t ucol, ustride, zcol, zstride;
+  uint32_t tlist;  // this warp's tail list (kTailListBytes), see tail_phase_coop
+};
+
+// Raw words -> normals in two phases (normals.cuh): the central formula for all draws of a
+// generator round, then the tail draws of the whole refill.
+//   central_round_planar : one generator round (8 steps), returns its tail bits; tail bit j
+//                          marks word j of the refill
+//   tail_phase_planar    : every lane loops over its OWN tail draws, two per iteration
+//   tail_pair            : two tail draws -> their slots of the z ring
 template <int NORMAL_MODE>
 struct ZRing;
 
 template <>
 struct ZRing<HEXO_NORMAL_F32> {
   static constexpr int kBytesPerStep = 8;  // float2 (Z_V, Z_X)
-  static __device__ __forceinline__ void fill(const uint64_t (&o)[16], uint32_t wcol,
-                                              uint32_t wstride, uint32_t zcol, uint32_t zstride) {
-    uint32_t tails = 0;
-#pragma unroll
-    for (int s = 0; s < kStepsPerRound; ++s) {
-      float zv, zx;
-      bool t0, t1;
-      normal2_central_f32(o[2 * s], o[2 * s + 1], zv, zx, t0, t1);
-      sts_b64(zcol + s * zstride, pack2(zv, zx));
-      if (t0) tails |= 1u << (2 * s);
-      if (t1) tails |= 2u << (2 * s);
-    }
-    tail_phase(tails, wcol, wstride, zcol, zstride);
-  }
-  // central phase of one generator round (8 steps) whose first step lives at zcol0; returns the
-  // 16 tail bits of the round
-  static __device__ __forceinline__ uint32_t central_round(const uint64_t (&o)[16], uint32_t zcol0,
-                                                           uint32_t zstride) {
-    uint32_t tails = 0;
-#pragma unroll
-    for (int s = 0; s < kStepsPerRound; ++s) {
-      float zv, zx;
-      bool t0, t1;
-      normal2_central_f32(o[2 * s], o[2 * s + 1], zv, zx, t0, t1);
-      sts_b64(zcol0 + s * zstride, pack2(zv, zx));
-      if (t0) tails |= 1u << (2 * s);
-      if (t1) tails |= 2u << (2 * s);
-    }
-    return tails;
-  }
-  // one (central normals, tail flag) pair of a step, for kernels that spread the central phase
-  // over the step loop: returns the two tail bits
-  static __device__ __forceinline__ uint32_t central_step(uint32_t waddr, uint32_t zaddr) {
-    uint64_t w0, w1;
-    lds_b64x2(waddr, w0, w1);
-    float zv, zx;
-    bool t0, t1;
-    normal2_central_f32(w0, w1, zv, zx, t0, t1);
-    sts_b64(zaddr, pack2(zv, zx));
-    return (t0 ? 1u : 0u) | (t1 ? 2u : 0u);
-  }
-  // two tail draws per iteration: the two evaluations are independent, which hides the
-  // MUFU (lg2, sqrt, rcp) latencies of this otherwise serial loop
-  static __device__ __forceinline__ void tail_phase(uint32_t tails, uint32_t wcol,
-                                                    uint32_t wstride, uint32_t zcol,
-                                                    uint32_t zstride, uint32_t wplane = 8) {
-    while (tails) {
-      const int j0 = __ffs(tails) - 1;
-      tails &= tails - 1;
-      const bool two = tails != 0;
-      const int j1 = two ? __ffs(tails) - 1 : j0;
-      tails &= tails - 1;
-      const uint64_t w0 = lds_b64(wcol + (j0 >> 1) * wstride + (j0 & 1) * wplane);
-      const uint64_t w1 = lds_b64(wcol + (j1 >> 1) * wstride + (j1 & 1) * wplane);
-      float t0, t1;
-      float z0 = normal_tail_mid_f32(w0, t0), z1 = normal_tail_mid_f32(w1, t1);
-      if (fmaxf(t0, t1) > 25.0f) {  // far tail: essentially never
-        if (t0 > 25.0f) z0 = normal_tail_far_f32(w0, t0);
-        if (t1 > 25.0f) z1 = normal_tail_far_f32(w1, t1);
-      }
-      sts_f32(zcol + (j0 >> 1) * zstride + (j0 & 1) * 4, z0);
-      if (two) sts_f32(zcol + (j1 >> 1) * zstride + (j1 & 1) * 4, z1);
-    }
-  }
-  // ---- planar ring of the default kernel (RING steps per refill, a power of two) ------------
-  // Raw words live in two planes [variance words | spot words] of RING steps each, so word j of
-  // the refill (j = RING d + step, d = 0 variance / 1 spot) sits at wcol + j wstride; tail bit j
-  // marks that word.
   template <int RING>
   static __device__ __forceinline__ uint32_t central_round_planar(const uint64_t (&o)[16],
                                                                   int step0, uint32_t zcol,
@@ -239,28 +203,17 @@ struct ZRing<HEXO_NORMAL_F32> {
     }
     return tails;
   }
-  template <int RING>
-  static __device__ __forceinline__ void tail_phase_planar(uint32_t tails, uint32_t wcol,
-                                                           uint32_t wstride, uint32_t zcol,
-                                                           uint32_t zstride) {
-    constexpr int kLog = RING == 16 ? 4 : RING == 8 ? 3 : RING == 4 ? 2 : 1;
-    while (tails) {  // two tail draws per iteration (independent evaluations hide MUFU latency)
-      const uint32_t j0 = bfind32(tails);
-      const uint32_t b0 = 1u << j0, rest = tails ^ b0;
-      const bool two = rest != 0;
-      const uint32_t j1 = bfind32(two ? rest : b0);  // j0 again when it was the last one
-      tails = rest & ~(1u << j1);
-      const uint64_t w0 = lds_b64(wcol + j0 * wstride);
-      const uint64_t w1 = lds_b64(wcol + j1 * wstride);
-      float t0, t1;
-      float z0 = normal_tail_mid_f32(w0, t0), z1 = normal_tail_mid_f32(w1, t1);
-      if (fmaxf(t0, t1) > 25.0f) {  // far tail: essentially never
-        if (t0 > 25.0f) z0 = normal_tail_far_f32(w0, t0);
-        if (t1 > 25.0f) z1 = normal_tail_far_f32(w1, t1);
-      }
-      sts_f32(zcol + (j0 & (RING - 1)) * zstride + (j0 >> kLog) * 4, z0);
-      if (two) sts_f32(zcol + (j1 & (RING - 1)) * zstride + (j1 >> kLog) * 4, z1);
+  // two tail draws (words w0, w1; `two` false: w1 is w0 again) -> z ring slots za0, za1
+  static __device__ __forceinline__ void tail_pair(uint64_t w0, uint64_t w1, bool two, uint32_t za0,
+                                                   uint32_t za1) {
+    float t0, t1, z0, z1;
+    normal2_tail_mid_f32(w0, w1, z0, z1, t0, t1);
+    if (fmaxf(t0, t1) > 25.0f) {  // far tail: essentially never
+      if (t0 > 25.0f) z0 = normal_tail_far_f32(w0, t0);
+      if (t1 > 25.0f) z1 = normal_tail_far_f32(w1, t1);
     }
+    sts_f32(za0, z0);
+    if (two) sts_f32(za1, z1);
   }
   static __device__ __forceinline__ void get(uint32_t addr, double& zv, double& zx) {
     float a, b;
@@ -273,64 +226,6 @@ struct ZRing<HEXO_NORMAL_F32> {
 template <>
 struct ZRing<HEXO_NORMAL_F64> {
   static constexpr int kBytesPerStep = 16;  // double2 (Z_V, Z_X)
-  static __device__ __forceinline__ void fill(const uint64_t (&o)[16], uint32_t wcol,
-                                              uint32_t wstride, uint32_t zcol, uint32_t zstride) {
-    uint32_t tails = 0;
-#pragma unroll
-    for (int s = 0; s < kStepsPerRound; ++s) {
-      bool t0, t1;
-      const double zv = normal_central_f64(o[2 * s], t0);
-      const double zx = normal_central_f64(o[2 * s + 1], t1);
-      sts_f64x2(zcol + s * zstride, zv, zx);
-      if (t0) tails |= 1u << (2 * s);
-      if (t1) tails |= 2u << (2 * s);
-    }
-    tail_phase(tails, wcol, wstride, zcol, zstride);
-  }
-  static __device__ __forceinline__ uint32_t central_round(const uint64_t (&o)[16], uint32_t zcol0,
-                                                           uint32_t zstride) {
-    uint32_t tails = 0;
-#pragma unroll
-    for (int s = 0; s < kStepsPerRound; ++s) {
-      bool t0, t1;
-      const double zv = normal_central_f64(o[2 * s], t0);
-      const double zx = normal_central_f64(o[2 * s + 1], t1);
-      sts_f64x2(zcol0 + s * zstride, zv, zx);
-      if (t0) tails |= 1u << (2 * s);
-      if (t1) tails |= 2u << (2 * s);
-    }
-    return tails;
-  }
-  static __device__ __forceinline__ uint32_t central_step(uint32_t waddr, uint32_t zaddr) {
-    uint64_t w0, w1;
-    lds_b64x2(waddr, w0, w1);
-    bool t0, t1;
-    const double zv = normal_central_f64(w0, t0);
-    const double zx = normal_central_f64(w1, t1);
-    sts_f64x2(zaddr, zv, zx);
-    return (t0 ? 1u : 0u) | (t1 ? 2u : 0u);
-  }
-  static __device__ __forceinline__ void tail_phase(uint32_t tails, uint32_t wcol,
-                                                    uint32_t wstride, uint32_t zcol,
-                                                    uint32_t zstride, uint32_t wplane = 8) {
-    while (tails) {  // two tail draws per iteration, as in F32 mode
-      const int j0 = __ffs(tails) - 1;
-      tails &= tails - 1;
-      const bool two = tails != 0;
-      const int j1 = two ? __ffs(tails) - 1 : j0;
-      tails &= tails - 1;
-      const uint64_t w0 = lds_b64(wcol + (j0 >> 1) * wstride + (j0 & 1) * wplane);
-      const uint64_t w1 = lds_b64(wcol + (j1 >> 1) * wstride + (j1 & 1) * wplane);
-      double r0, r1;
-      double z0 = normal_tail_mid_f64(w0, r0), z1 = normal_tail_mid_f64(w1, r1);
-      if (fmax(r0, r1) > Ppnd::SPLIT2) {  // far tail: essentially never
-        if (r0 > Ppnd::SPLIT2) z0 = normal_tail_far_f64(w0, r0);
-        if (r1 > Ppnd::SPLIT2) z1 = normal_tail_far_f64(w1, r1);
-      }
-      sts_f64(zcol + (j0 >> 1) * zstride + (j0 & 1) * 8, z0);
-      if (two) sts_f64(zcol + (j1 >> 1) * zstride + (j1 & 1) * 8, z1);
-    }
-  }
   template <int RING>
   static __device__ __forceinline__ uint32_t central_round_planar(const uint64_t (&o)[16],
                                                                   int step0, uint32_t zcol,
@@ -348,33 +243,123 @@ struct ZRing<HEXO_NORMAL_F64> {
     }
     return tails;
   }
-  template <int RING>
-  static __device__ __forceinline__ void tail_phase_planar(uint32_t tails, uint32_t wcol,
-                                                           uint32_t wstride, uint32_t zcol,
-                                                           uint32_t zstride) {
-    constexpr int kLog = RING == 16 ? 4 : RING == 8 ? 3 : RING == 4 ? 2 : 1;
-    while (tails) {
-      const uint32_t j0 = bfind32(tails);
-      const uint32_t b0 = 1u << j0, rest = tails ^ b0;
-      const bool two = rest != 0;
-      const uint32_t j1 = bfind32(two ? rest : b0);  // j0 again when it was the last one
-      tails = rest & ~(1u << j1);
-      const uint64_t w0 = lds_b64(wcol + j0 * wstride);
-      const uint64_t w1 = lds_b64(wcol + j1 * wstride);
-      double r0, r1;
-      double z0 = normal_tail_mid_f64(w0, r0), z1 = normal_tail_mid_f64(w1, r1);
-      if (fmax(r0, r1) > Ppnd::SPLIT2) {  // far tail: essentially never
-        if (r0 > Ppnd::SPLIT2) z0 = normal_tail_far_f64(w0, r0);
-        if (r1 > Ppnd::SPLIT2) z1 = normal_tail_far_f64(w1, r1);
-      }
-      sts_f64(zcol + (j0 & (RING - 1)) * zstride + (j0 >> kLog) * 8, z0);
-      if (two) sts_f64(zcol + (j1 & (RING - 1)) * zstride + (j1 >> kLog) * 8, z1);
+  static __device__ __forceinline__ void tail_pair(uint64_t w0, uint64_t w1, bool two, uint32_t za0,
+                                                   uint32_t za1) {
+    double r0, r1;
+    double z0 = normal_tail_mid_f64(w0, r0), z1 = normal_tail_mid_f64(w1, r1);
+    if (fmax(r0, r1) > Ppnd::SPLIT2) {  // far tail: essentially never
+      if (r0 > Ppnd::SPLIT2) z0 = normal_tail_far_f64(w0, r0);
+      if (r1 > Ppnd::SPLIT2) z1 = normal_tail_far_f64(w1, r1);
     }
+    sts_f64(za0, z0);
+    if (two) sts_f64(za1, z1);
   }
   static __device__ __forceinline__ void get(uint32_t addr, double& zv, double& zx) {
     lds_f64x2(addr, zv, zx);
   }
 };
+
+// Tail phase, per lane: each lane loops over its own tail draws, two per iteration (independent
+// evaluations hide the MUFU latencies).  The warp runs as long as its unluckiest lane.
+template <int NORMAL_MODE, int RING>
+__device__ __forceinline__ void tail_phase_planar(uint32_t tails, const RingAddr& ra) {
+  using Ring = ZRing<NORMAL_MODE>;
+  constexpr int kLog = RING == 16 ? 4 : RING == 8 ? 3 : RING == 4 ? 2 : 1;
+  constexpr uint32_t kHalf = Ring::kBytesPerStep / 2;
+  while (tails) {
+    const uint32_t j0 = bfind32(tails);
+    const uint32_t b0 = 1u << j0, rest = tails ^ b0;
+    const bool two = rest != 0;
+    const uint32_t j1 = bfind32(two ? rest : b0);  // j0 again when it was the last one
+    tails = rest & ~(1u << j1);
+    const uint64_t w0 = lds_b64(ra.ucol + j0 * ra.ustride);
+    const uint64_t w1 = lds_b64(ra.ucol + j1 * ra.ustride);
+    Ring::tail_pair(w0, w1, two, ra.zcol + (j0 & (RING - 1)) * ra.zstride + (j0 >> kLog) * kHalf,
+                    ra.zcol + (j1 & (RING - 1)) * ra.zstride + (j1 >> kLog) * kHalf);
+  }
+}
+
+// Tail phase, warp-cooperative: the tail draws of all 32 lanes (154 +- 11 of the 1024 draws of a
+// 16-step refill) are listed in shared memory and dealt out evenly, so the warp runs
+// ceil(total / 64) two-draw iterations (3) instead of as many as its unluckiest lane needs (4.8
+// on average).  All 32 lanes of the warp must call this together.
+//   list entry = (owner lane << 5) | word index j, 16 bits; lane l takes entries [l c, l c + c),
+//   c = 2 ceil(total / 64), so that lanes working side by side read different owners' columns
+template <int NORMAL_MODE, int RING>
+__device__ __forceinline__ void tail_phase_coop(uint32_t tails, const RingAddr& ra, uint32_t lane) {
+  using Ring = ZRing<NORMAL_MODE>;
+  constexpr int kLog = RING == 16 ? 4 : RING == 8 ? 3 : RING == 4 ? 2 : 1;
+  constexpr uint32_t kHalf = Ring::kBytesPerStep / 2;
+  const uint32_t cnt = __popc(tails);
+  uint32_t incl = cnt;  // inclusive prefix sum of the lanes' counts
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t up = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= (uint32_t)d) incl += up;
+  }
+  const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+  if (total > (uint32_t)kTailListCap) {  // warp-uniform; never in practice
+    tail_phase_planar<NORMAL_MODE, RING>(tails, ra);
+    return;
+  }
+  uint32_t la = ra.tlist + 2 * (incl - cnt);
+  const uint32_t tag = lane << 5;
+  while (tails) {
+    const uint32_t j = bfind32(tails);
+    tails ^= 1u << j;
+    sts_u16(la, tag | j);
+    la += 2;
+  }
+  __syncwarp();
+  const uint32_t c = ((total + 63) >> 6) << 1;
+  const uint32_t ubase = ra.ucol - 8 * lane, zbase = ra.zcol - Ring::kBytesPerStep * lane;
+  uint32_t i = lane * c;
+  for (uint32_t t = 0; t < c; t += 2, i += 2) {
+    if (i < total) {
+      const uint32_t e2 = lds_u32(ra.tlist + 2 * i);
+      const bool two = i + 1 < total;
+      const uint32_t e0 = e2 & 0xffffu, e1 = two ? e2 >> 16 : e0;
+      const uint32_t l0 = e0 >> 5, j0 = e0 & 31u, l1 = e1 >> 5, j1 = e1 & 31u;
+      const uint64_t w0 = lds_b64(ubase + 8 * l0 + j0 * ra.ustride);
+      const uint64_t w1 = lds_b64(ubase + 8 * l1 + j1 * ra.ustride);
+      Ring::tail_pair(w0, w1, two,
+                      zbase + Ring::kBytesPerStep * l0 + (j0 & (RING - 1)) * ra.zstride +
+                          (j0 >> kLog) * kHalf,
+                      zbase + Ring::kBytesPerStep * l1 + (j1 & (RING - 1)) * ra.zstride +
+                          (j1 >> kLog) * kHalf);
+    }
+  }
+  __syncwarp();
+}
+
+// Refill of a thread's whole ring: RING / 8 generator rounds -- raw words parked in their planes,
+// central normals in the z ring -- then ONE tail phase over all their draws.  `o` holds the
+// first round already when have_first.  This is the code the path kernel runs per refill AND
+// what hexo_gpu_normals_from_words exposes for the parity test of the transform.
+template <int NORMAL_MODE, class Gen>
+__device__ __forceinline__ void ring_refill(Gen& rng, uint64_t (&o)[16], bool have_first,
+                                            const RingAddr& ra, uint32_t lane) {
+  using Ring = ZRing<NORMAL_MODE>;
+  constexpr int kRing = ring_steps(NORMAL_MODE);
+  const uint32_t uplane = kRing * ra.ustride;
+  uint32_t tails = 0;
+#pragma unroll
+  for (int r = 0; r < kRing / kStepsPerRound; ++r) {
+    if (r > 0 || !have_first) rng.round(o);
+    const uint32_t u0 = ra.ucol + r * kStepsPerRound * ra.ustride;
+#pragma unroll
+    for (int s = 0; s < kStepsPerRound; ++s) {
+      sts_b64(u0 + s * ra.ustride, o[2 * s]);
+      sts_b64(u0 + s * ra.ustride + uplane, o[2 * s + 1]);
+    }
+    tails |= Ring::template central_round_planar<kRing>(o, r * kStepsPerRound, ra.zcol, ra.zstride);
+  }
+#if HEXO_TAIL_COOP
+  tail_phase_coop<NORMAL_MODE, kRing>(tails, ra, lane);
+#else
+  tail_phase_planar<NORMAL_MODE, kRing>(tails, ra);
+#endif
+}
 
 // Payoff accumulation of one maturity with the control variate c = final value - S: the walk
 // over the warp's 32 final values also collects sum pf c per strike, and lane 0 adds sum c and
@@ -441,7 +426,6 @@ heston_qe_paths_kernel(const __grid_constant__ PathArgs a) {
   // pays four moves to line the words up in an aligned register quad) and a warp's 64-bit
   // accesses touch consecutive 8-byte slots
   const uint32_t zstride = pin32(Ring::kBytesPerStep * T), ustride = pin32(8 * T);
-  const uint32_t uplane = kRing * ustride;  // = 8 kRing T
   const uint32_t ucol = pin32(smem_addr(sp) + 8 * tid);  // variance word of step 0
   sp += (size_t)16 * kRing * T;
   const uint32_t zcol = pin32(smem_addr(sp) + Ring::kBytesPerStep * tid);
@@ -451,6 +435,8 @@ heston_qe_paths_kernel(const __grid_constant__ PathArgs a) {
   sp += 32 * 8;
   double* fvbuf = reinterpret_cast<double*>(sp) + 32 * warp;
   sp += (size_t)32 * 8 * nwarps;
+  const uint32_t tlist = pin32(smem_addr(sp) + kTailListBytes * warp);
+  sp += (size_t)kTailListBytes * nwarps;
 #define HEXO_N_ACC (CV ? 3 * a.n_opts + 2 * a.n_seg : 2 * a.n_opts)
   // The plain case spells its offsets out as the 64-bit product chain it has always been: the
   // register allocation of the whole kernel (114 registers, 1 % faster step loop) hangs on it.
@@ -482,31 +468,11 @@ heston_qe_paths_kernel(const __grid_constant__ PathArgs a) {
           : 0u;
 
   Gen rng;  // Shishua (the reference's generator) or PhiloxGen (optional counter mode)
-  // one generator round -> raw words and central normals of steps [8 r, 8 r + 8) of the ring;
-  // returns the round's 16 tail bits
-  auto park_round = [&](const uint64_t (&o)[16], int r) -> uint32_t {
-    const uint32_t u0 = ucol + r * kStepsPerRound * ustride;
-#pragma unroll
-    for (int s = 0; s < kStepsPerRound; ++s) {
-      sts_b64(u0 + s * ustride, o[2 * s]);
-      sts_b64(u0 + s * ustride + uplane, o[2 * s + 1]);
-    }
-    return Ring::template central_round_planar<kRing>(o, r * kStepsPerRound, zcol, zstride);
-  };
-  // refill the whole ring: kRing / 8 generator rounds, then ONE tail phase over all their draws
-  auto refill = [&](uint64_t (&o)[16], bool have_first) {
-    uint32_t tails = 0;
-#pragma unroll
-    for (int r = 0; r < kRing / kStepsPerRound; ++r) {
-      if (r > 0 || !have_first) rng.round(o);
-      tails |= park_round(o, r);
-    }
-    Ring::template tail_phase_planar<kRing>(tails, ucol, ustride, zcol, zstride);
-  };
+  const RingAddr ra = {ucol, ustride, zcol, zstride, tlist};
   {
     uint64_t o[16];
     rng.init(a.seed, sid, 0, 0, o);
-    refill(o, true);
+    ring_refill<NORMAL_MODE>(rng, o, true, ra, lane);
   }
   uint32_t pos = 0;  // next unread step of the round
   __syncthreads();   // exptab
@@ -566,9 +532,12 @@ heston_qe_paths_kernel(const __grid_constant__ PathArgs a) {
           bool first = true;
           while (count) {
             if (pos == kRing) {
-              if (!a.dev_no_refill) {
+#ifdef HEXO_DEV_PROBES
+              if (!a.dev_no_refill)
+#endif
+              {
                 uint64_t o[16];
-                refill(o, false);
+                ring_refill<NORMAL_MODE>(rng, o, false, ra, lane);
               }
               pos = 0;
             }

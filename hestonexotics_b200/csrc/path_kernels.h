@@ -5,13 +5,10 @@
 // sees function pointers.
 #pragma once
 #include "path_kernel.cuh"
-#include "path_kernel_il.cuh"
-#include "path_kernel_ws.cuh"
 
 namespace hexo {
 
 typedef void (*PathKernel)(const PathArgs);
-typedef void (*PathKernelWs)(const PathArgs, const uint32_t);
 
 // payoff: hexo_payoff, normal_mode: hexo_normal_mode, segs: kSegsGlobal / kSegsInline / kSegsSingle
 PathKernel path_kernel_shishua(int payoff, int normal_mode, int segs);     // the default
@@ -20,15 +17,15 @@ PathKernel path_kernel_philox(int payoff, int normal_mode, int segs, bool cv);
 // HEXO_DRIFT_MARTINGALE (path_kernels_*_mart*.cu)
 PathKernel path_kernel_shishua_mart(int payoff, int normal_mode, int segs, bool cv);
 PathKernel path_kernel_philox_mart(int payoff, int normal_mode, int segs, bool cv);
-// experimental variants (HEXO_WS=1 / HEXO_IL=1)
-PathKernelWs path_kernel_ws(int payoff, int normal_mode, bool inline_segs);
-PathKernel path_kernel_il(int payoff, int normal_mode, bool inline_segs);
 
 // shared by the selector translation units
-template <class Gen, bool CV, bool MART = false>
+// SINGLE: also instantiate the single-maturity variant (constants as uniform-register operands);
+// the optional Philox families do without it and run one maturity through kSegsInline
+template <class Gen, bool CV, bool MART = false, bool SINGLE = true>
 inline PathKernel select_path_kernel(int payoff, int normal_mode, int segs) {
+  constexpr int kOne = SINGLE ? kSegsSingle : kSegsInline;
 #define HEXO_PICK(P, N)                                                             \
-  (segs == kSegsSingle   ? heston_qe_paths_kernel<P, N, kSegsSingle, Gen, CV, MART> \
+  (segs == kSegsSingle   ? heston_qe_paths_kernel<P, N, kOne, Gen, CV, MART>        \
    : segs == kSegsInline ? heston_qe_paths_kernel<P, N, kSegsInline, Gen, CV, MART> \
                          : heston_qe_paths_kernel<P, N, kSegsGlobal, Gen, CV, MART>)
   if (payoff == HEXO_PAYOFF_ASIAN)

@@ -71,7 +71,11 @@ __device__ __forceinline__ double qe_variance_quad(const SegConst& g, const doub
   const double w = fma(m, m, -s2h);                         // m^2 (1 - psi/2)
   const double sw = fast_sqrt(w);                           // a b^2
   const double dm = m - sw;                                 // a
-  const double me = fast_sqrt(fma(sw, dm, kFm.tiny));       // a b; sw dm >= 0, kept off exact 0
+  // a b.  sw dm >= 0 in exact arithmetic; with psi below ~1e-15 (sigma ~1e-8) the rounded sw can
+  // exceed m by an ulp and the product is -1e-19: fast_sqrt_signed seeds from |x|, so the result
+  // is -3e-10 instead of NaN -- against sw ~ m that is the degenerate a = 0 which the
+  // reference's a = m/(1+b^2) rounds to.  The 1e-300 keeps the argument off exact zero.
+  const double me = fast_sqrt_signed(fma(sw, dm, kFm.tiny));
   mid.m = m;
   mid.s2h = s2h;
   // :63  psi >= 1.5  <=>  3 w <= s^2/2.  Read off the sign of 3 w - s^2/2 on the integer pipe

@@ -190,51 +190,57 @@ def shard_range(n_streams: int, rank: int, world_size: int):
     return begin, base + (1 if rank < rem else 0)
 
 
+def _gpu_shard(rq: "_Request", begin: int, count: int, world: int, stats):
+    """This rank's stream range on its own GPU (torch's current device and stream); returns the
+    shard's sums as a device tensor, ready for the all-reduce."""
+    import torch
+    lib = _lib.load()
+    dev = torch.cuda.current_device()
+    _lib.check(lib.hexo_gpu_init(dev))
+    sums_t = torch.zeros(rq.n_sums, dtype=torch.float64, device=f"cuda:{dev}")
+    if count > 0:
+        stream = torch.cuda.current_stream().cuda_stream
+        _lib.check(lib.hexo_gpu_price_shard_device(
+            C.byref(rq.req), begin, count, C.c_void_p(sums_t.data_ptr()), C.c_void_p(stream),
+            C.byref(stats)))
+    return sums_t
+
+
+def _reduce_shards(rq: "_Request", shard_fn, group=None) -> PriceResult:
+    """The multi-rank host logic: split the job's streams over the ranks of `group`, let
+    `shard_fn(rq, begin, count, world, stats)` produce this rank's sums (a torch tensor on any
+    device), combine them with ONE all-reduce and finish on the host.  price_distributed passes
+    the GPU shard; the CPU tests (gloo) pass a stand-in so that this logic runs without a GPU."""
+    import torch.distributed as dist
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    if rq.req.n_streams == 0:
+        rq.req.n_streams = _lib.load().hexo_gpu_default_streams(rq.req.n_paths, rq.n_opts, world)
+    stats = _lib.HexoGpuStats()
+    begin, count = shard_range(rq.req.n_streams, rank, world)
+    sums_t = shard_fn(rq, begin, count, world, stats)
+    dist.all_reduce(sums_t, op=dist.ReduceOp.SUM, group=group)
+    sums = sums_t.cpu().numpy()
+    mean, se = _finish(rq, sums)
+    return PriceResult(mean, se, sums, int(rq.req.n_paths), int(rq.req.n_streams),
+                       int(stats.steps_per_path), int(rq.req.n_paths) * int(rq.req.steps), 0.0,
+                       int(stats.grid), int(stats.block))
+
+
 def price_distributed(scheme, p: HParams, S: float, all_chains: Sequence[OptionsChain],
                       n_simulations: int, n_opts: Optional[int], steps: int, *, seed: int = 1,
                       normal_mode="f32", n_streams: int = 0, rng="shishua",
-                      time_grid="reference", control_variate=None, drift="reference", group=None,
-                      _shard_sums=None) -> PriceResult:
+                      time_grid="reference", control_variate=None, drift="reference",
+                      group=None) -> PriceResult:
     """price<Scheme>() sharded over the ranks of a torch.distributed group.
 
     Every rank runs a disjoint range of RNG streams on its own GPU and the
     payoff sums (2*n_opts doubles, a few more with a control variate) are combined with ONE
-    all-reduce (NCCL over NVLink when
-    the group's backend is nccl).  All ranks return the same prices.  `_shard_sums`
-    (tests only) replaces the GPU shard computation so the sharding logic can be
-    exercised with gloo on CPU.
+    all-reduce (NCCL over NVLink when the group's backend is nccl).  All ranks return the same
+    prices.
     """
-    import torch
-    import torch.distributed as dist
-
-    rank, world = dist.get_rank(group), dist.get_world_size(group)
     rq = _Request(scheme, p, S, all_chains, n_simulations, n_opts, steps, seed, normal_mode,
                   n_streams, rng, time_grid, control_variate, drift)
-    stats = _lib.HexoGpuStats()
-    if _shard_sums is None:
-        lib = _lib.load()
-        dev = torch.cuda.current_device()
-        _lib.check(lib.hexo_gpu_init(dev))
-        if rq.req.n_streams == 0:
-            rq.req.n_streams = lib.hexo_gpu_default_streams(rq.req.n_paths, rq.n_opts, world)
-        begin, count = shard_range(rq.req.n_streams, rank, world)
-        sums_t = torch.zeros(rq.n_sums, dtype=torch.float64, device=f"cuda:{dev}")
-        if count > 0:
-            stream = torch.cuda.current_stream().cuda_stream
-            _lib.check(lib.hexo_gpu_price_shard_device(
-                C.byref(rq.req), begin, count, C.c_void_p(sums_t.data_ptr()), C.c_void_p(stream),
-                C.byref(stats)))
-    else:
-        if rq.req.n_streams == 0:
-            raise ValueError("n_streams must be given with a custom shard function")
-        begin, count = shard_range(rq.req.n_streams, rank, world)
-        sums_t = torch.from_numpy(np.asarray(_shard_sums(rq, begin, count), dtype=np.float64).copy())
-    dist.all_reduce(sums_t, op=dist.ReduceOp.SUM, group=group)
-    sums = sums_t.cpu().numpy()
-    mean, se = _finish(rq, sums)
-    return PriceResult(mean, se, sums, int(n_simulations), int(rq.req.n_streams),
-                       int(stats.steps_per_path), int(n_simulations) * int(steps), 0.0,
-                       int(stats.grid), int(stats.block))
+    return _reduce_shards(rq, _gpu_shard, group)
 
 
 def schedule(expiries: Sequence[float], steps: int, time_grid="reference"):

@@ -28,7 +28,8 @@
 extern "C" {
 #endif
 
-#define HEXO_GPU_ABI_VERSION 3 /* 2: rng_mode, schedule_mode, control_variate; 3: drift_mode */
+#define HEXO_GPU_ABI_VERSION 4 /* 2: rng_mode, schedule_mode, control_variate; 3: drift_mode;
+                                 * 4: normals_from_words, replay steps_used_out, geometric control */
 
 typedef enum {
   HEXO_OK = 0,
@@ -240,6 +241,14 @@ int hexo_gpu_philox_streams(uint64_t seed, uint64_t first_stream, uint32_t n_str
 /* ---- K3: uniform map and inverse normal (RNG.cpp:31, as241.f90:15-119) ------ */
 int hexo_gpu_u64_to_unit(const uint64_t *bits_in, double *u_out, size_t n);
 int hexo_gpu_ppnd16(const double *u_in, double *z_out, size_t n, int normal_mode);
+/* The same transform EXACTLY as the fused kernel K1 runs it (RNG.cpp:31,39 + as241.f90:85-118
+ * on raw generator words): the batched central phase and the warp-cooperative tail phase of
+ * the kernel's shared-memory ring, fed with caller-supplied words instead of generator rounds.
+ * z_out[i] is the normal K1 would hand to the stepper for word words_in[i]; compare with
+ * ppnd16(u64_to_unit(word)).  hexo_gpu_ppnd16 above evaluates the scalar routine, which K1 does
+ * not call. */
+int hexo_gpu_normals_from_words(const uint64_t *words_in, double *z_out, size_t n,
+                                int normal_mode);
 
 /* ---- K4: tape replay of stepper + payoff policy ------------------------------
  * tape[path][step][3] = {Z_V, U_V, Z_X} (normals/uniform the reference's RNG
@@ -247,7 +256,8 @@ int hexo_gpu_ppnd16(const double *u_in, double *z_out, size_t n, int normal_mode
  * the policy's final_value (Asian average / interpolated X_T).  Uses
  * req->{p,S,payoff,n_chains,expiries,steps}; strikes are not needed. */
 int hexo_gpu_replay(const hexo_price_request *req, const double *tape, uint64_t n_paths,
-                    uint32_t tape_steps, double *finals_out);
+                    uint32_t tape_steps, double *finals_out,
+                    uint32_t *steps_used_out /* stepper calls per path, or NULL */);
 
 /* ---- semi-analytic European benchmark (host only) ---------
  * The Heston characteristic function with its analytic gradient and the SWIFT

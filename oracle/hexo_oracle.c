@@ -119,6 +119,12 @@ static double ppnd16(double p, int normal_mode) {
                                           : oracle_ppnd16_f32(p, &ifault);
 }
 
+/* RNG::setup_u + RNG::setup_g on caller-supplied raw words (src/RNG.cpp:31,39): the oracle
+ * side of hexo_gpu_normals_from_words */
+void oracle_normals_from_words(const uint64_t *words, double *z, size_t n, int normal_mode) {
+  for (size_t i = 0; i < n; ++i) z[i] = ppnd16(oracle_u64_to_unit(words[i]), normal_mode);
+}
+
 /* ========================================================================== */
 /* RNG wrapper: two ring buffers fed by ONE shishua state                     */
 /* ========================================================================== */

@@ -62,6 +62,9 @@ double oracle_u64_to_unit(uint64_t x);
 /* ---- AS241 / PPND16, src/as241.f90:15-119 -------------------------------- */
 double oracle_ppnd16_f64(double p, int *ifault);
 double oracle_ppnd16_f32(double p, int *ifault); /* as built */
+/* z[i] = ppnd16(u64_to_unit(words[i])): RNG::setup_u + setup_g (src/RNG.cpp:31,39) on
+ * caller-supplied raw words */
+void oracle_normals_from_words(const uint64_t *words, double *z, size_t n, int normal_mode);
 /* sums of the decimal coefficients, to compare with as241.f90:45,64,83 */
 void oracle_ppnd16_hash_sums(double out[3]);
 

@@ -58,6 +58,8 @@ def oracle() -> C.CDLL:
         o.oracle_ppnd16_f64.argtypes = [C.c_double, C.POINTER(C.c_int)]
         o.oracle_ppnd16_f32.restype = C.c_double
         o.oracle_ppnd16_f32.argtypes = [C.c_double, C.POINTER(C.c_int)]
+        o.oracle_normals_from_words.restype = None
+        o.oracle_normals_from_words.argtypes = [C.POINTER(C.c_uint64), dp, C.c_size_t, C.c_int]
         o.oracle_rng_new.restype = C.c_void_p
         o.oracle_rng_new.argtypes = [C.c_size_t, C.c_uint, C.c_int]
         o.oracle_rng_grand.restype = C.c_double
@@ -214,6 +216,15 @@ def ppnd16(p: np.ndarray, normal_mode) -> np.ndarray:
     f = o.oracle_ppnd16_f64 if normal_mode == NORMAL_F64 else o.oracle_ppnd16_f32
     ifault = C.c_int(0)
     return np.array([f(float(x), C.byref(ifault)) for x in p], dtype=np.float64)
+
+
+def normals_from_words(words: np.ndarray, normal_mode) -> np.ndarray:
+    """ppnd16(u64_to_unit(word)) for every raw word (RNG.cpp:31,39), vectorised in the oracle."""
+    words = np.ascontiguousarray(words, dtype=np.uint64)
+    z = np.zeros(len(words))
+    oracle().oracle_normals_from_words(words.ctypes.data_as(C.POINTER(C.c_uint64)),
+                                       z.ctypes.data_as(dp), len(words), int(normal_mode))
+    return z
 
 
 def rng_sequence(size, seed, kinds, normal_mode=NORMAL_F32) -> np.ndarray:

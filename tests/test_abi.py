@@ -32,7 +32,7 @@ def test_library_exports_every_declared_symbol(hexo_lib):
     assert host == sorted(_lib.HOST_SYMBOLS)
     for n in host:
         assert hasattr(hexo_lib, n), f"{n} declared in include/hexo_gpu.h but not exported"
-    assert hexo_lib.hexo_gpu_abi_version() == 3
+    assert hexo_lib.hexo_gpu_abi_version() == 4
 
 
 def test_struct_layout_matches_header(hexo_lib):

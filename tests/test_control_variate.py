@@ -1,8 +1,10 @@
 """Control variate (the reference only suggests one, src/inc/HSimulation.h:51):
-c = final value - S (arithmetic average or terminal spot minus the initial spot) has mean zero
-because the simulated model has no drift.  The kernel accumulates [sum pf c] per option and
-[sum c | sum c^2] per maturity next to the plain sums; hexo_gpu_finish turns them into
-price = mean(pf) - beta mean(c)."""
+c = final value - S (arithmetic average or terminal spot minus the initial spot).  The simulated
+model has no drift, so E[X_j] = S and E[c] follows from the weights the payoff policy applies:
+0 for the European payoff and for the full trapezoid rule, S (W/T - 1) on the reference's grid,
+whose last trapezoid is replaced when the steps land on the expiry (SURVEY finding 6).  The
+kernel accumulates [sum pf c] per option and [sum c | sum c^2] per maturity next to the plain
+sums; hexo_gpu_finish turns them into price = mean(pf) - beta (mean(c) - E[c])."""
 import ctypes as C
 
 import numpy as np
@@ -11,9 +13,28 @@ import pytest
 import oracle_api as oa
 
 
-def cv_estimate(sums, n_paths, offsets):
-    """Reference implementation of the estimator in numpy (what hexo_gpu_finish must compute)."""
+def control_means(payoff, S, expiries, steps, exact=False):
+    """E[c] per maturity, restated in numpy from the step schedule: the sum of the trapezoid
+    weights the Asian policy actually applies (AsianContract.h:25-34, HSimulation.tpp:42-44)."""
+    import hestonexotics_b200 as hx
+    if payoff != oa.ASIAN:
+        return np.zeros(len(expiries))
+    sched = hx.schedule(expiries, steps, "exact" if exact else "reference")
+    out, weight = [], 0.0
+    for k, (n, h, w, T) in enumerate(sched):
+        if n > 0:
+            if k > 0:   # the trapezoid of the step that crossed the previous expiry
+                weight += sched[k - 1][1] if exact else h
+            weight += h * (n - 1)
+        out.append(S * ((weight + (h if exact else 0.0)) / T - 1.0))
+    return np.array(out)
+
+
+def cv_estimate(sums, n_paths, offsets, ec=None):
+    """Reference implementation of the estimator in numpy (what hexo_gpu_finish must compute);
+    ec = known mean of the control per maturity."""
     n_opts, n_ch = int(offsets[-1]), len(offsets) - 1
+    ec = np.zeros(n_ch) if ec is None else ec
     sp, sq, sx = sums[:n_opts], sums[n_opts:2 * n_opts], sums[2 * n_opts:3 * n_opts]
     sc, sc2 = sums[3 * n_opts:3 * n_opts + n_ch], sums[3 * n_opts + n_ch:]
     n = float(n_paths)
@@ -26,7 +47,7 @@ def cv_estimate(sums, n_paths, offsets):
             var = (sq[j] - n * m * m) / (n - 1)
             cov = (sx[j] - n * m * mc) / (n - 1)
             beta = cov / vc
-            prices[j] = m - beta * mc
+            prices[j] = m - beta * (mc - ec[k])
             se[j] = np.sqrt(max(0.0, var - beta * cov) / n)
     return prices, se
 
@@ -44,7 +65,7 @@ def test_finish_matches_numpy_estimator(hexo_lib):
                           None, 30, 4, "f64", 64, control_variate="underlying")
     assert hexo_lib.hexo_gpu_sums_len(C.byref(rq.req)) == sums.size == 3 * 5 + 2 * 2
     prices, se = pricing._finish(rq, sums)
-    want_p, want_se = cv_estimate(sums, n, c.offsets)
+    want_p, want_se = cv_estimate(sums, n, c.offsets, control_means(oa.ASIAN, 100.0, T, 30))
     np.testing.assert_allclose(prices, want_p, rtol=1e-12)
     np.testing.assert_allclose(se, want_se, rtol=1e-9)
     # and it is a variance reduction: compare with the plain standard error
@@ -55,6 +76,38 @@ def test_finish_matches_numpy_estimator(hexo_lib):
     assert np.all(se <= se0) and np.all(se[:3] < 0.75 * se0[:3])   # little to gain far out of the money
     assert np.all(np.abs(prices - p0) < 4 * se0)
     np.testing.assert_allclose(p0, sums[:5] / n, rtol=1e-15)
+
+
+@pytest.mark.parametrize("steps,exact", [(64, False), (252, False), (64, True)])
+def test_control_mean_on_the_reference_grid(hexo_lib, steps, exact):
+    """on a power-of-two step count the reference's grid replaces the last trapezoid,
+    E[average] = S (1 - 1/steps), so the control has mean -S/steps (-1.5625 at 64 steps), not 0.
+    The estimator must subtract the known mean: the simulated mean of c agrees with it and the
+    control-variate price agrees with the plain one (host only: oracle sums + hexo_gpu_finish)."""
+    import hestonexotics_b200 as hx
+    from hestonexotics_b200 import pricing
+    T, K, n = [1.0], [[80.0, 100.0]], 200_000
+    c = oa.Contract(oa.ASIAN, T, K, steps)
+    sums = c.price_stream_cv(21, n, 256, normal_mode=oa.NORMAL_F64, exact_grid=exact)
+    ec = control_means(oa.ASIAN, 100.0, T, steps, exact)
+    if not exact and steps == 64:
+        assert abs(ec[0] + 100.0 / 64) < 1e-12
+    if exact:
+        assert abs(ec[0]) < 1e-12
+    mean_c = sums[3 * 2] / n
+    se_c = np.sqrt((sums[3 * 2 + 1] / n - mean_c ** 2) / n)
+    assert abs(mean_c - ec[0]) < 4 * se_c + 0.01          # + the QE drift error of E[X_j] = S
+    chains = [hx.OptionsChain.from_strikes(1.0, K[0])]
+    grid = "exact" if exact else "reference"
+    rq = pricing._Request(hx.HQEAnderson(hx.AAsianCallNonAdaptive), hx.HParams(*oa.DEFAULT_PARAMS),
+                          100.0, chains, n, None, steps, 21, "f64", 256, time_grid=grid,
+                          control_variate="underlying")
+    plain = pricing._Request(hx.HQEAnderson(hx.AAsianCallNonAdaptive), hx.HParams(*oa.DEFAULT_PARAMS),
+                             100.0, chains, n, None, steps, 21, "f64", 256, time_grid=grid)
+    p_cv, se_cv = pricing._finish(rq, sums)
+    p0, se0 = pricing._finish(plain, sums[:4])
+    assert np.all(np.abs(p_cv - p0) < 4 * se0), (p_cv, p0, se0)   # was 64 standard errors apart
+    assert se_cv[0] < 0.3 * se0[0]
 
 
 def test_oracle_cv_sums_extend_the_plain_sums():
@@ -89,17 +142,20 @@ def _cv_worker(rank, world):
         T, K, steps, n = [0.5, 1.0], [[100.0], [90.0, 110.0]], 12, 4001
         c = oa.Contract(oa.ASIAN, T, K, steps)
 
-        def shard(rq, begin, count):
-            return c.price_stream_cv(int(rq.req.seed), int(rq.req.n_paths), int(rq.req.n_streams),
-                                     begin, count, normal_mode=oa.NORMAL_F64)
-        res = hx.price_distributed(hx.HQEAnderson(hx.AAsianCallNonAdaptive),
-                                   hx.HParams(*oa.DEFAULT_PARAMS), 100.0,
-                                   [hx.OptionsChain.from_strikes(t, k) for t, k in zip(T, K)], n,
-                                   None, steps, seed=8, normal_mode="f64", n_streams=37,
-                                   control_variate="underlying", _shard_sums=shard)
+        import torch
+
+        def shard(rq, begin, count, world_, stats):   # the oracle stands in for the GPU shard
+            return torch.from_numpy(c.price_stream_cv(
+                int(rq.req.seed), int(rq.req.n_paths), int(rq.req.n_streams), begin, count,
+                normal_mode=oa.NORMAL_F64))
+        rq = pricing._Request(hx.HQEAnderson(hx.AAsianCallNonAdaptive),
+                              hx.HParams(*oa.DEFAULT_PARAMS), 100.0,
+                              [hx.OptionsChain.from_strikes(t, k) for t, k in zip(T, K)], n,
+                              None, steps, 8, "f64", 37, control_variate="underlying")
+        res = pricing._reduce_shards(rq, shard)
         full = c.price_stream_cv(8, n, 37, normal_mode=oa.NORMAL_F64)
         np.testing.assert_allclose(res.sums, full, rtol=1e-12, atol=1e-9)
-        want, _ = cv_estimate(full, n, c.offsets)
+        want, _ = cv_estimate(full, n, c.offsets, control_means(oa.ASIAN, 100.0, T, steps))
         np.testing.assert_allclose(res.prices, want, rtol=1e-9)
     finally:
         dist.destroy_process_group()
@@ -144,7 +200,8 @@ def test_gpu_cv_sums_match_oracle(gpu, name, payoff, T, K, steps, n_paths, n_str
                           n_paths, None, steps, **kw)
     np.testing.assert_array_equal(res.sums[:2 * n], plain.sums)
     if n_paths > 100:
-        wp, wse = cv_estimate(res.sums, n_paths, c.offsets)
+        wp, wse = cv_estimate(res.sums, n_paths, c.offsets,
+                              control_means(payoff, 100.0, T, steps, exact))
         np.testing.assert_allclose(res.prices, wp, rtol=1e-10)
         np.testing.assert_allclose(res.stderr, wse, rtol=1e-8, atol=1e-14)
 

@@ -29,16 +29,20 @@ def _worker(rank, world, port, ret):
     try:
         c = oa_.Contract(oa_.ASIAN, [0.5, 1.0], [[95.0, 100.0], [105.0]], 24)
 
-        def shard(rq, begin, count):
+        import torch
+        from hestonexotics_b200 import pricing
+
+        def shard(rq, begin, count, world, stats):   # the oracle stands in for the GPU shard
             sm, sq = c.price_stream(int(rq.req.seed), int(rq.req.n_paths), int(rq.req.n_streams),
                                     begin, count)
-            return np.concatenate([sm, sq])
+            return torch.from_numpy(np.concatenate([sm, sq]))
 
         p = hx.HParams(*oa_.DEFAULT_PARAMS)
         chains = [hx.OptionsChain.from_strikes(0.5, [95.0, 100.0]),
                   hx.OptionsChain.from_strikes(1.0, [105.0])]
-        res = hx.price_distributed(hx.HQEAnderson(hx.AAsianCallNonAdaptive), p, 100.0, chains,
-                                   701, 3, 24, seed=3, n_streams=13, _shard_sums=shard)
+        rq = pricing._Request(hx.HQEAnderson(hx.AAsianCallNonAdaptive), p, 100.0, chains, 701, 3,
+                              24, 3, "f32", 13)
+        res = pricing._reduce_shards(rq, shard)   # what hx.price_distributed runs, GPU shard aside
         ret[rank] = (res.prices.tolist(), res.stderr.tolist(), res.sums.tolist())
     finally:
         dist.destroy_process_group()

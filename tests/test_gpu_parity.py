@@ -146,9 +146,10 @@ def test_replay_final_values(gpu, payoff, expiries, steps, params):
                              hx.HParams(*params), 100.0, chains_of(expiries, [[100.0]] * len(expiries)),
                              n_paths, None, steps, 1, "f64", 0)
     got = np.zeros((n_paths, len(expiries)))
+    used = C.c_uint32(0)
     rc = gpu.hexo_gpu_replay(C.byref(rq.req), tape.ctypes.data_as(_lib.c_double_p), n_paths,
-                             tape.shape[1], got.ctypes.data_as(_lib.c_double_p))
-    assert rc == nsteps, gpu.hexo_gpu_last_error()
+                             tape.shape[1], got.ctypes.data_as(_lib.c_double_p), C.byref(used))
+    assert rc == 0 and used.value == nsteps, gpu.hexo_gpu_last_error()
     rel = np.abs(got - want) / np.abs(want)
     assert rel.max() <= 1e-12, rel.max()
 
@@ -158,7 +159,7 @@ def test_replay_tape_too_short(gpu):
     tape = np.zeros((4, 100, 3))
     out = np.zeros((4, 1))
     rc = gpu.hexo_gpu_replay(C.byref(rq.req), tape.ctypes.data_as(_lib.c_double_p), 4, 100,
-                             out.ctypes.data_as(_lib.c_double_p))
+                             out.ctypes.data_as(_lib.c_double_p), None)
     assert rc == -6
 
 
@@ -209,24 +210,50 @@ def test_fused_kernel_sums_vs_oracle_streams(gpu, case, mode, tol):
     assert res.path_steps == n_paths * steps
 
 
-@pytest.mark.parametrize("case", [c for c in FUSED_CASES if c[0] in
-                                  ("asian_1", "euro_same_step", "asian_chain_70_strikes", "exp_branch",
-                                   "twelve_chains", "more_streams_than_a_block")],
-                         ids=lambda c: c[0])
-@pytest.mark.parametrize("variant", ["HEXO_WS", "HEXO_IL"])
-def test_experimental_kernel_variants_same_sums(gpu, case, variant, monkeypatch):
-    """HEXO_WS=1 selects the producer/consumer kernel (path_kernel_ws.cuh), HEXO_IL=1 the
-    interleaved look-ahead kernel (path_kernel_il.cuh): same streams, same arithmetic, so the
-    same sums as the oracle."""
-    monkeypatch.setenv(variant, "1")
-    _, scheme, payoff, T, K, steps, params, n_paths, n_streams = case
-    c = oa.Contract(payoff, T, K, steps, params)
-    sm, sq = c.price_stream(seed=7, n_paths=n_paths, n_streams=n_streams, normal_mode=oa.NORMAL_F64)
-    res = hx.price_full(scheme, hx.HParams(*params), 100.0, chains_of(T, K), n_paths, c.n_opts,
-                        steps, seed=7, normal_mode="f64", n_streams=n_streams)
-    n = c.n_opts
-    assert (np.abs(res.sums[:n] - sm) / np.maximum(np.abs(sm), 1e-300)).max() <= 1e-10
-    assert (np.abs(res.sums[n:] - sq) / np.maximum(np.abs(sq), 1e-300)).max() <= 2e-10
+@pytest.mark.parametrize("var", ["HEXO_NO_REFILL", "HEXO_BLOCK", "HEXO_WS", "HEXO_IL"])
+def test_development_env_vars_do_not_reach_the_product_library(gpu, var, monkeypatch):
+    """The probes of the development build (`python -m hestonexotics_b200.build --dev`,
+    -DHEXO_DEV_PROBES) are not compiled into the shipped library: a stray environment variable
+    must not change a single bit of the sums."""
+    args = (ASIAN, P0, 100.0, chains_of([0.5, 1.0], [[95.0, 100.0], [105.0]]), 30011, 3, 70)
+    want = hx.price_full(*args, seed=3, n_streams=1500)
+    monkeypatch.setenv(var, "64" if var == "HEXO_BLOCK" else "1")
+    got = hx.price_full(*args, seed=3, n_streams=1500)
+    assert np.array_equal(got.sums, want.sums)
+    assert (got.grid, got.block) == (want.grid, want.block)
+
+
+def test_plans_with_different_option_counts_coexist(gpu):
+    """cudaFuncAttributeMaxDynamicSharedMemorySize belongs to the kernel, not to a plan: a plan
+    with a wide chain must still launch after a narrower plan of the same kernel was created."""
+    lib = gpu
+    wide = hx.pricing._Request(ASIAN, P0, 100.0, chains_of([1.0], [list(np.linspace(70, 130, 60))]),
+                               20000, 60, 32, 1, "f32", 2048)
+    narrow = hx.pricing._Request(ASIAN, P0, 100.0, chains_of([1.0], [[100.0]]), 20000, 1, 32, 1,
+                                 "f32", 2048)
+    pa, pb = C.c_void_p(), C.c_void_p()
+    _lib.check(lib.hexo_gpu_plan_create(C.byref(wide.req), 0, 2048, C.byref(pa)))
+    _lib.check(lib.hexo_gpu_plan_create(C.byref(narrow.req), 0, 2048, C.byref(pb)))
+    for plan, rq in ((pa, wide), (pb, narrow), (pa, wide)):
+        _lib.check(lib.hexo_gpu_plan_launch(plan, None, None))   # fails with "invalid value" if
+        sums = np.zeros(rq.n_sums)                               # the attribute was lowered
+        _lib.check(lib.hexo_gpu_price_shard(C.byref(rq.req), 0, 2048,
+                                            sums.ctypes.data_as(_lib.c_double_p), None))
+        assert np.all(sums[:rq.n_opts] >= 0.0)
+    _lib.check(lib.hexo_gpu_plan_destroy(pa))
+    _lib.check(lib.hexo_gpu_plan_destroy(pb))
+
+
+def test_tiny_sigma_stays_finite(gpu):
+    """sigma = 1e-8: psi ~ 1e-15, where the rounded sqrt(m^2 - s^2/2) can exceed m by an ulp
+    (ADVICE r1): prices must stay finite and sit on the deterministic-variance (Black-Scholes)
+    value."""
+    p = hx.HParams(0.04, 0.04, -0.7, 2.0, 1e-8)
+    r = hx.price_full(EURO, p, 100.0, chains_of([1.0], [[100.0]]), 200_000, 1, 1000, seed=1,
+                      normal_mode="f64")
+    from math import erf, sqrt
+    bs = 100.0 * (erf(0.1 / sqrt(2.0)))   # S (N(d1) - N(d2)), d1 = -d2 = 0.1 at vol 20 %
+    assert np.isfinite(r.prices[0]) and abs(r.prices[0] - bs) <= 4 * r.stderr[0]
 
 
 def test_sharded_streams_add_up(gpu):

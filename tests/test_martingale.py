@@ -142,9 +142,10 @@ def test_replay_final_values_martingale(gpu, payoff, expiries, steps, params):
                              _chains(expiries, [[100.0]] * len(expiries)), n_paths, None, steps, 1,
                              "f64", 0, drift="martingale")
     got = np.zeros((n_paths, len(expiries)))
+    used = C.c_uint32(0)
     rc = gpu.hexo_gpu_replay(C.byref(rq.req), tape.ctypes.data_as(_lib.c_double_p), n_paths,
-                             tape.shape[1], got.ctypes.data_as(_lib.c_double_p))
-    assert rc == nsteps, gpu.hexo_gpu_last_error()
+                             tape.shape[1], got.ctypes.data_as(_lib.c_double_p), C.byref(used))
+    assert rc == 0 and used.value == nsteps, gpu.hexo_gpu_last_error()
     rel = np.abs(got - want) / np.abs(want)
     assert rel.max() <= 1e-12, rel.max()
 

@@ -239,3 +239,13 @@ def test_replay_matches_stream_convention():
     sm, _ = c.price_stream(9, n_paths, 1, normal_mode=oa.NORMAL_F64)
     pay = np.maximum(finals - 100.0, 0.0).sum(axis=0)
     assert np.allclose(pay, sm, rtol=1e-13)
+
+
+def test_normals_from_words_is_the_scalar_composition():
+    """oracle_normals_from_words = ppnd16(u64_to_unit(word)) (RNG.cpp:31,39), both modes."""
+    words = oa.shishua_bytes((5, 0, 0, 0), 128 * 16).view(np.uint64)
+    words = np.concatenate([words, np.array([0, 2 ** 64 - 1, 2 ** 63], dtype=np.uint64)])
+    for mode in (oa.NORMAL_F32, oa.NORMAL_F64):
+        z = oa.normals_from_words(words, mode)
+        assert np.array_equal(z, oa.ppnd16(oa.u64_to_unit(words), mode))
+        assert z[-3] == 0.0 and z[-2] == 0.0 and z[-1] == 0.0
