@@ -26,11 +26,12 @@ ABI_SYMBOLS = (
     "hexo_gpu_normals_from_words",
 )
 # host-only semi-analytic benchmark functions of the same library (no hexo_gpu_ prefix)
-HOST_SYMBOLS = ("hexo_heston_chf", "hexo_swift_default_params", "hexo_swift_price_chain")
+HOST_SYMBOLS = ("hexo_heston_chf", "hexo_heston_cumulants", "hexo_swift_default_params",
+                "hexo_swift_price_chain")
 
 HEXO_OK = 0
 PAYOFF_ASIAN, PAYOFF_EUROPEAN = 0, 1
-NORMAL_F32, NORMAL_F64 = 0, 1
+NORMAL_F32, NORMAL_F64, NORMAL_F32_PPND7 = 0, 1, 2
 RNG_SHISHUA, RNG_PHILOX = 0, 1
 
 c_double_p = C.POINTER(C.c_double)
@@ -134,6 +135,7 @@ def load() -> C.CDLL:
     lib.hexo_gpu_measure_fp64_peak.argtypes = [c_double_p, C.POINTER(C.c_float)]
     lib.hexo_heston_chf.argtypes = [C.POINTER(HexoHParams), C.c_double, C.c_double, C.c_double,
                                     c_double_p]
+    lib.hexo_heston_cumulants.argtypes = [C.POINTER(HexoHParams), C.c_double, c_double_p]
     lib.hexo_swift_default_params.argtypes = [C.POINTER(HexoHParams), C.c_double, C.c_double,
                                               C.c_double, C.c_double, C.c_double, C.c_double,
                                               C.POINTER(HexoSwiftParams)]

@@ -357,8 +357,15 @@ static int check_request(const hexo_price_request* r, bool need_strikes) {
   if (r->steps == 0) return fail(HEXO_ERR_INVALID_ARGUMENT, "steps must be > 0");
   if (r->payoff != HEXO_PAYOFF_ASIAN && r->payoff != HEXO_PAYOFF_EUROPEAN)
     return fail(HEXO_ERR_INVALID_ARGUMENT, "unknown payoff %d", r->payoff);
-  if (r->normal_mode != HEXO_NORMAL_F32 && r->normal_mode != HEXO_NORMAL_F64)
+  if (r->normal_mode != HEXO_NORMAL_F32 && r->normal_mode != HEXO_NORMAL_F64 &&
+      r->normal_mode != HEXO_NORMAL_F32_PPND7)
     return fail(HEXO_ERR_INVALID_ARGUMENT, "unknown normal_mode %d", r->normal_mode);
+  if (r->normal_mode == HEXO_NORMAL_F32_PPND7 &&
+      (r->rng_mode != HEXO_RNG_SHISHUA || r->control_variate != HEXO_CV_NONE ||
+       r->drift_mode != HEXO_DRIFT_REFERENCE))
+    return fail(HEXO_ERR_INVALID_ARGUMENT,
+                "HEXO_NORMAL_F32_PPND7 is built for the shishua generator, the reference drift "
+                "and plain sums only");
   if (r->rng_mode != HEXO_RNG_SHISHUA && r->rng_mode != HEXO_RNG_PHILOX)
     return fail(HEXO_ERR_INVALID_ARGUMENT, "unknown rng_mode %d", r->rng_mode);
   if (r->schedule_mode != HEXO_SCHEDULE_REFERENCE && r->schedule_mode != HEXO_SCHEDULE_EXACT)
@@ -433,6 +440,21 @@ static int build_segments(const hexo_price_request* r, bool with_strikes,
     g.A = g.K2 + .5 * g.K3;  // HEXO_DRIFT_MARTINGALE (Andersen 2008, Prop. 9)
     g.A2 = 2. * g.A;
     g.K1m = -.5 * g.K3;
+    // The division-free variance step (qe.cuh) forms a = m - sqrt(m^2 - s^2/2) by subtraction:
+    // its relative rounding error is ~4e-16 / psi, psi ~ sigma^2 h / V, and it reaches the
+    // log-spot through rho/sigma (K1, K2).  Per step that is about
+    // |rho| 2.8e-16 V^1.5 / (sigma^2 sqrt(h)): 5e-17 for the BASELINE parameters, 1e-12 at
+    // sigma = 0.01 -- and O(1) at sigma = 1e-8, where the reference's a = m / (1 + b^2) is still
+    // fine.  Refuse the (near-deterministic-variance) corner instead of pricing it inaccurately.
+    {
+      const double vmax = std::max(r->p.v_0, theta);
+      const double est = fabs(rho) * 2.8e-16 * vmax * sqrt(vmax) / (eps * eps * sqrt(h));
+      if (est > 1e-9)
+        return fail(HEXO_ERR_INVALID_ARGUMENT,
+                    "sigma = %g is too small for this step width (h = %g): the division-free QE "
+                    "step would lose ~%.1e per step in the log-spot; sigma >= %.2e is supported here",
+                    eps, h, est, eps * sqrt(est / 1e-9));
+    }
     g.first_opt = with_strikes ? r->strike_offsets[k] : 0;
     g.n_strikes = with_strikes ? r->strike_offsets[k + 1] - r->strike_offsets[k] : 0;
     g.pad = 0;
@@ -539,6 +561,7 @@ static PathKernel pick_kernel(int payoff, int normal_mode, uint32_t n_seg, int r
     return rng_mode == HEXO_RNG_PHILOX ? path_kernel_philox_mart(payoff, normal_mode, segs, cv)
                                        : path_kernel_shishua_mart(payoff, normal_mode, segs, cv);
   if (rng_mode == HEXO_RNG_PHILOX) return path_kernel_philox(payoff, normal_mode, segs, cv);
+  if (normal_mode == HEXO_NORMAL_F32_PPND7) return path_kernel_shishua_ppnd7(payoff, segs);
   return cv ? path_kernel_shishua_cv(payoff, normal_mode, segs)
             : path_kernel_shishua(payoff, normal_mode, segs);
 }
@@ -649,7 +672,7 @@ static int plan_fill(const hexo_price_request* r, uint64_t stream_begin, uint64_
 #ifdef HEXO_DEV_PROBES
   {
     const char* e = getenv("HEXO_NO_REFILL");
-    a.dev_no_refill = (e && atoi(e) != 0) ? 1u : 0u;
+    a.dev_no_refill = e ? (uint32_t)atoi(e) : 0u;
   }
 #endif
   a.gacc = acc_in_smem ? nullptr : reinterpret_cast<double*>(base + off_gacc);
@@ -1134,7 +1157,8 @@ int hexo_gpu_ppnd16(const double* u_in, double* z_out, size_t n, int normal_mode
 int hexo_gpu_normals_from_words(const uint64_t* words_in, double* z_out, size_t n, int normal_mode) {
   if (!words_in || !z_out || n == 0)
     return fail(HEXO_ERR_INVALID_ARGUMENT, "normals_from_words: bad args");
-  if (normal_mode != HEXO_NORMAL_F32 && normal_mode != HEXO_NORMAL_F64)
+  if (normal_mode != HEXO_NORMAL_F32 && normal_mode != HEXO_NORMAL_F64 &&
+      normal_mode != HEXO_NORMAL_F32_PPND7)
     return fail(HEXO_ERR_INVALID_ARGUMENT, "unknown normal_mode %d", normal_mode);
   int rc = ensure_context();
   if (rc) return rc;
@@ -1154,15 +1178,12 @@ int hexo_gpu_normals_from_words(const uint64_t* words_in, double* z_out, size_t 
     e = cudaMemcpy(dw + n, pad.data(), pad.size() * 8, cudaMemcpyHostToDevice);
   if (e == cudaSuccess) {
     const unsigned grid = (unsigned)((n_chunks + block - 1) / block);
-    if (normal_mode == HEXO_NORMAL_F64) {
-      e = cudaFuncSetAttribute(normals_from_words_kernel<1>,
-                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_ctx.smem_optin);
-      if (e == cudaSuccess) normals_from_words_kernel<1><<<grid, block, smem>>>(dw, dz, n_chunks);
-    } else {
-      e = cudaFuncSetAttribute(normals_from_words_kernel<0>,
-                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_ctx.smem_optin);
-      if (e == cudaSuccess) normals_from_words_kernel<0><<<grid, block, smem>>>(dw, dz, n_chunks);
-    }
+    auto kern = normal_mode == HEXO_NORMAL_F64         ? normals_from_words_kernel<HEXO_NORMAL_F64>
+                : normal_mode == HEXO_NORMAL_F32_PPND7 ? normals_from_words_kernel<HEXO_NORMAL_F32_PPND7>
+                                                       : normals_from_words_kernel<HEXO_NORMAL_F32>;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)g_ctx.smem_optin);
+    if (e == cudaSuccess) kern<<<grid, block, smem>>>(dw, dz, n_chunks);
     if (e == cudaSuccess) e = cudaGetLastError();
   }
   if (e == cudaSuccess) e = cudaMemcpy(z_out, dz, n * 8, cudaMemcpyDeviceToHost);

@@ -59,6 +59,26 @@ __device__ __forceinline__ uint64_t horner8x2(uint64_t r, float c7, float c6, fl
   return v;
 }
 
+__device__ __forceinline__ uint64_t horner4x2(uint64_t r, float c3, float c2, float c1, float c0) {
+  uint64_t v = ffma2(HEXO_BC(c3), r, HEXO_BC(c2));
+  v = ffma2(v, r, HEXO_BC(c1));
+  return ffma2(v, r, HEXO_BC(c0));
+}
+
+// AS241's single-precision routine PPND7 (Wichura 1988: the same algorithm with 7-digit
+// coefficients; its printed hash sums are AB 32.3184577772, CD 15.7614929821, checked in
+// tests/test_ppnd16.py): degree 3/3 and 3/2 rational functions on the same regions as PPND16.
+// The reference carries only PPND16 (src/as241.f90) and evaluates it in single precision as
+// built; PPND7 is what the algorithm itself prescribes for single precision.  Optional mode
+// HEXO_NORMAL_F32_PPND7; the far tail (p < 1.4e-11) keeps PPND16's E / F coefficients.
+struct Ppnd7 {
+  static constexpr float A0 = 3.3871327179e+00f, A1 = 5.0434271938e+01f, A2 = 1.5929113202e+02f,
+                         A3 = 5.9109374720e+01f, B1 = 1.7895169469e+01f, B2 = 7.8757757664e+01f,
+                         B3 = 6.7187563600e+01f;
+  static constexpr float C0 = 1.4234372777e+00f, C1 = 2.7568153900e+00f, C2 = 1.3067284816e+00f,
+                         C3 = 1.7023821103e-01f, D1 = 7.3700164250e-01f, D2 = 1.2021132975e-01f;
+};
+
 __device__ __forceinline__ float mufu_lg2(float x) {
   float y;
   asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -98,6 +118,8 @@ static __device__ __noinline__ float ppnd_far_tail_f32(float q, float t) {
 // Phase 1 (F32 mode): the central formula for two draws at once (as241.f90:88-92).
 // tail0/tail1 are set when |q| > 0.425; such draws get their value from
 // normal_tail_f32 afterwards (z0/z1 then hold a finite placeholder).
+//   P7: AS241's single-precision routine PPND7 instead of PPND16's coefficients rounded to single
+template <bool P7 = false>
 __device__ __forceinline__ void normal2_central_f32(uint64_t w0, uint64_t w1, float& z0, float& z1,
                                                     bool& tail0, bool& tail1) {
   using P = Ppnd;
@@ -111,10 +133,12 @@ __device__ __forceinline__ void normal2_central_f32(uint64_t w0, uint64_t w1, fl
   tail0 = fabsf(q0) > (float)P::SPLIT1;
   tail1 = fabsf(q1) > (float)P::SPLIT1;
   const uint64_t rc = pack2(fmaf(-q0, q0, (float)P::CONST1), fmaf(-q1, q1, (float)P::CONST1));
-  uint64_t num = horner8x2(rc, (float)P::A7, (float)P::A6, (float)P::A5, (float)P::A4,
-                           (float)P::A3, (float)P::A2, (float)P::A1, (float)P::A0);
-  const uint64_t den = horner8x2(rc, (float)P::B7, (float)P::B6, (float)P::B5, (float)P::B4,
-                                 (float)P::B3, (float)P::B2, (float)P::B1, 1.0f);
+  uint64_t num = P7 ? horner4x2(rc, Ppnd7::A3, Ppnd7::A2, Ppnd7::A1, Ppnd7::A0)
+                    : horner8x2(rc, (float)P::A7, (float)P::A6, (float)P::A5, (float)P::A4,
+                                (float)P::A3, (float)P::A2, (float)P::A1, (float)P::A0);
+  const uint64_t den = P7 ? horner4x2(rc, Ppnd7::B3, Ppnd7::B2, Ppnd7::B1, 1.0f)
+                          : horner8x2(rc, (float)P::B7, (float)P::B6, (float)P::B5, (float)P::B4,
+                                      (float)P::B3, (float)P::B2, (float)P::B1, 1.0f);
   num = fmul2(num, q2);
   float d0, d1;
   unpack2(den, d0, d1);
@@ -151,6 +175,7 @@ __device__ __forceinline__ float normal_tail_mid_f32(uint64_t w, float& t) {
 // packed form done for both at once: v 2^-32, t, r - 1.6, the C / D Horner chains (14 FFMA2
 // instead of 28 FFMA) and the final product.  fma.rn.f32x2 is two IEEE fmas, so each half is
 // bit-identical to the scalar routine.
+template <bool P7 = false>
 __device__ __forceinline__ void normal2_tail_mid_f32(uint64_t w0, uint64_t w1, float& z0, float& z1,
                                                      float& t0, float& t1) {
   using P = Ppnd;
@@ -165,10 +190,13 @@ __device__ __forceinline__ void normal2_tail_mid_f32(uint64_t w0, uint64_t w1, f
                             HEXO_BC(22.180709777918249f));
   unpack2(t2, t0, t1);
   const uint64_t r = fadd2(pack2(mufu_sqrt(t0), mufu_sqrt(t1)), HEXO_BC(-(float)P::CONST2));
-  const uint64_t num = horner8x2(r, (float)P::C7, (float)P::C6, (float)P::C5, (float)P::C4,
-                                 (float)P::C3, (float)P::C2, (float)P::C1, (float)P::C0);
-  const uint64_t den = horner8x2(r, (float)P::D7, (float)P::D6, (float)P::D5, (float)P::D4,
-                                 (float)P::D3, (float)P::D2, (float)P::D1, 1.0f);
+  const uint64_t num = P7 ? horner4x2(r, Ppnd7::C3, Ppnd7::C2, Ppnd7::C1, Ppnd7::C0)
+                          : horner8x2(r, (float)P::C7, (float)P::C6, (float)P::C5, (float)P::C4,
+                                      (float)P::C3, (float)P::C2, (float)P::C1, (float)P::C0);
+  const uint64_t den =
+      P7 ? ffma2(ffma2(HEXO_BC(Ppnd7::D2), r, HEXO_BC(Ppnd7::D1)), r, HEXO_BC(1.0f))
+         : horner8x2(r, (float)P::D7, (float)P::D6, (float)P::D5, (float)P::D4, (float)P::D3,
+                     (float)P::D2, (float)P::D1, 1.0f);
   float d0, d1, a0, a1;
   unpack2(den, d0, d1);
   unpack2(fmul2(num, pack2(mufu_rcp(d0), mufu_rcp(d1))), a0, a1);

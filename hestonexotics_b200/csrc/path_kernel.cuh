@@ -74,8 +74,9 @@ struct PathArgs {
   // maturity: 3 n_opts + 2 n_seg.
   double* partials;  // [gridDim.x][n_acc]
 #ifdef HEXO_DEV_PROBES
-  uint32_t dev_no_refill;  // development build only (HEXO_NO_REFILL=1): reuse the first refill
-                           // forever, i.e. time the FP64 step loop alone (wrong prices!)
+  uint32_t dev_no_refill;  // development build only (wrong prices!).  HEXO_NO_REFILL=1: the step
+                           // loop alone (ring reused with flipped signs); 2: generator and
+                           // normal transform alone (the step loop only sums the normals)
 #endif
   double* gacc;      // nullptr: per-warp accumulators in shared memory; else zero-initialised
                      // [gridDim.x][warps][n_acc] in device memory (large option chains,
@@ -183,8 +184,8 @@ struct RingAddr {
 template <int NORMAL_MODE>
 struct ZRing;
 
-template <>
-struct ZRing<HEXO_NORMAL_F32> {
+template <bool P7>
+struct ZRingF32 {
   static constexpr int kBytesPerStep = 8;  // float2 (Z_V, Z_X)
   template <int RING>
   static __device__ __forceinline__ uint32_t central_round_planar(const uint64_t (&o)[16],
@@ -196,7 +197,7 @@ struct ZRing<HEXO_NORMAL_F32> {
     for (int s = 0; s < kStepsPerRound; ++s) {
       float zv, zx;
       bool t0, t1;
-      normal2_central_f32(o[2 * s], o[2 * s + 1], zv, zx, t0, t1);
+      normal2_central_f32<P7>(o[2 * s], o[2 * s + 1], zv, zx, t0, t1);
       sts_b64(zcol + (step0 + s) * zstride, pack2(zv, zx));
       if (t0) tails |= 1u << (step0 + s);
       if (t1) tails |= 1u << (RING + step0 + s);
@@ -207,7 +208,7 @@ struct ZRing<HEXO_NORMAL_F32> {
   static __device__ __forceinline__ void tail_pair(uint64_t w0, uint64_t w1, bool two, uint32_t za0,
                                                    uint32_t za1) {
     float t0, t1, z0, z1;
-    normal2_tail_mid_f32(w0, w1, z0, z1, t0, t1);
+    normal2_tail_mid_f32<P7>(w0, w1, z0, z1, t0, t1);
     if (fmaxf(t0, t1) > 25.0f) {  // far tail: essentially never
       if (t0 > 25.0f) z0 = normal_tail_far_f32(w0, t0);
       if (t1 > 25.0f) z1 = normal_tail_far_f32(w1, t1);
@@ -222,6 +223,11 @@ struct ZRing<HEXO_NORMAL_F32> {
     zx = (double)b;
   }
 };
+
+template <>
+struct ZRing<HEXO_NORMAL_F32> : ZRingF32<false> {};
+template <>
+struct ZRing<HEXO_NORMAL_F32_PPND7> : ZRingF32<true> {};
 
 template <>
 struct ZRing<HEXO_NORMAL_F64> {
@@ -533,7 +539,20 @@ heston_qe_paths_kernel(const __grid_constant__ PathArgs a) {
           while (count) {
             if (pos == kRing) {
 #ifdef HEXO_DEV_PROBES
-              if (!a.dev_no_refill)
+              if (a.dev_no_refill == 1) {
+                // probe "step loop alone": no generator, no transform -- the ring is reused with
+                // every normal's sign flipped (the draws stay N(0,1), the paths stay in their
+                // usual regime; reusing them unchanged drives V into the psi >= 1.5 branch)
+                for (int s = 0; s < kRing; ++s) {
+                  const uint32_t za = zcol + s * zstride;
+                  if (NORMAL_MODE == HEXO_NORMAL_F64) {
+                    sts_b64(za, lds_b64(za) ^ 0x8000000000000000ull);
+                    sts_b64(za + 8, lds_b64(za + 8) ^ 0x8000000000000000ull);
+                  } else {
+                    sts_b64(za, lds_b64(za) ^ 0x8000000080000000ull);
+                  }
+                }
+              } else
 #endif
               {
                 uint64_t o[16];
@@ -564,6 +583,12 @@ heston_qe_paths_kernel(const __grid_constant__ PathArgs a) {
             for (; m; --m, za += zstride) {
               double zv, zx;
               Ring::get(za, zv, zx);
+#ifdef HEXO_DEV_PROBES
+              if (a.dev_no_refill == 2) {  // probe "generator + transform alone": trivial consumer
+                sumX += zv + zx;
+                continue;
+              }
+#endif
               // Second half of the previous step and first half of this one, straight-line
               // parts first: two independent dependency chains in ONE basic block.  The rare
               // cases of both (|log-return| > 0.08; psi >= 1.5) share a single branch behind

@@ -12,6 +12,7 @@ typedef void (*PathKernel)(const PathArgs);
 
 // payoff: hexo_payoff, normal_mode: hexo_normal_mode, segs: kSegsGlobal / kSegsInline / kSegsSingle
 PathKernel path_kernel_shishua(int payoff, int normal_mode, int segs);     // the default
+PathKernel path_kernel_shishua_ppnd7(int payoff, int segs);  // HEXO_NORMAL_F32_PPND7, plain sums
 PathKernel path_kernel_shishua_cv(int payoff, int normal_mode, int segs);  // + control variate
 PathKernel path_kernel_philox(int payoff, int normal_mode, int segs, bool cv);
 // HEXO_DRIFT_MARTINGALE (path_kernels_*_mart*.cu)
@@ -19,14 +20,18 @@ PathKernel path_kernel_shishua_mart(int payoff, int normal_mode, int segs, bool 
 PathKernel path_kernel_philox_mart(int payoff, int normal_mode, int segs, bool cv);
 
 // shared by the selector translation units
-// SINGLE: also instantiate the single-maturity variant (constants as uniform-register operands);
-// the optional Philox families do without it and run one maturity through kSegsInline
-template <class Gen, bool CV, bool MART = false, bool SINGLE = true>
+// VARIANTS: which of the three sources of per-maturity constants get their own instantiation
+// (each costs 4 kernels per family): 3 = single-maturity, parameter-bank and device-memory variants
+// (the default family); 2 = single-maturity + device memory; 1 = device memory only (the optional
+// Philox families).  In the step loop the parameter-bank and device-memory variants are the
+// same code -- both pin the constants in registers.
+template <class Gen, bool CV, bool MART = false, int VARIANTS = 3>
 inline PathKernel select_path_kernel(int payoff, int normal_mode, int segs) {
-  constexpr int kOne = SINGLE ? kSegsSingle : kSegsInline;
+  constexpr int kOne = VARIANTS >= 2 ? kSegsSingle : kSegsGlobal;
+  constexpr int kFew = VARIANTS >= 3 ? kSegsInline : kSegsGlobal;
 #define HEXO_PICK(P, N)                                                             \
   (segs == kSegsSingle   ? heston_qe_paths_kernel<P, N, kOne, Gen, CV, MART>        \
-   : segs == kSegsInline ? heston_qe_paths_kernel<P, N, kSegsInline, Gen, CV, MART> \
+   : segs == kSegsInline ? heston_qe_paths_kernel<P, N, kFew, Gen, CV, MART>        \
                          : heston_qe_paths_kernel<P, N, kSegsGlobal, Gen, CV, MART>)
   if (payoff == HEXO_PAYOFF_ASIAN)
     return normal_mode == HEXO_NORMAL_F64 ? HEXO_PICK(HEXO_PAYOFF_ASIAN, 1)

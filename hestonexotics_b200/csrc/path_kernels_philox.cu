@@ -2,6 +2,6 @@
 #include "path_kernels.h"
 namespace hexo {
 PathKernel path_kernel_philox_plain(int payoff, int normal_mode, int segs) {
-  return select_path_kernel<PhiloxGen, false, false, false>(payoff, normal_mode, segs);
+  return select_path_kernel<PhiloxGen, false, false, 1>(payoff, normal_mode, segs);
 }
 }  // namespace hexo

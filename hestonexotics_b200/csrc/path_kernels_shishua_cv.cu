@@ -2,6 +2,6 @@
 #include "path_kernels.h"
 namespace hexo {
 PathKernel path_kernel_shishua_cv(int payoff, int normal_mode, int segs) {
-  return select_path_kernel<Shishua, true>(payoff, normal_mode, segs);
+  return select_path_kernel<Shishua, true, false, 2>(payoff, normal_mode, segs);
 }
 }  // namespace hexo

@@ -5,6 +5,8 @@
 // analytic parameter gradient and the SWIFT (Shannon wavelet inverse Fourier)
 // pricer, without FFTW or Eigen.  Restates, in our own code:
 //   HDistribution::chf / chf_chf_grad / cumulants / int_error  src/HDistribution.cpp:8-113
+//     (same functions, own derivation: decaying-exponential form of the Riccati solution with
+//     one directional-derivative routine; cumulants from the moment cascade of the model)
 //   SwiftParameters                                             src/SWIFT.cpp:18-35
 //   SWIFT::SWIFT (density coefficients via two Fourier sums)    src/SWIFT.cpp:37-79
 //   SWIFT::CacheEntry (prices and gradients of one chain)       src/SWIFT.cpp:102-118
@@ -25,116 +27,170 @@ namespace swift {
 using cd = std::complex<double>;
 static const cd I(0.0, 1.0);
 
-// intermediate terms of the characteristic function (Cui et al. form,
-// arXiv:2103.01570), src/HDistribution.cpp:12-27
-struct ChfTerms {
-  cd xi, d, sinh_v, cosh_v, A1, A2, A, B, D;
-  double exp_kappa_tau;
+// ---------------------------------------------------------------------------------------------
+// Characteristic function and parameter gradient.
+//
+// The reference evaluates chf(u) = E[exp(-i u x_tau)], x the log-return at r = 0, in the
+// sinh / cosh arrangement of Cui et al. with a hand-expanded derivative per parameter
+// (src/HDistribution.cpp:12-88).  Same function here, derived from the Riccati solution in
+// its decaying-exponential form.  With s = -u,
+//     f = s^2 + i s,   beta = kappa - rho sigma i s,   d = sqrt(beta^2 + sigma^2 f)  (Re d >= 0),
+//     e = exp(-d tau),  c = beta - d,  N = d (1 + e) + beta (1 - e),
+// and because (beta - d)(beta + d) = -sigma^2 f the two pieces of the exponent collapse to
+//     ln chf = kappa theta / sigma^2 * G  -  v_0 f H,
+//     G = c tau - 2 ln(N / (2 d)),     H = (1 - e) / N.
+// Only e = exp(-d tau) with Re d >= 0 appears, so nothing overflows for large |u| tau, and
+// N / (2 d) -> 1 as u -> 0, so the principal logarithm is the continuous branch.
+//
+// Gradient: v_0 and theta enter linearly.  rho, kappa and sigma enter through beta and d only,
+// so ONE routine differentiates (G, H) along a direction (d beta, d(sigma^2 f)/2):
+//     d' = (beta beta' + [sigma] sigma f) / d,          e' = -tau e d',
+//     N' = d' (1 + e) + beta' (1 - e) + c tau e d',
+//     G' = (beta' - d') tau - 2 (N'/N - d'/d),          H' = (tau e d' N - (1 - e) N') / N^2.
+// No division by u anywhere (the reference's B_kappa has one), so u = 0 is a regular point.
+// ---------------------------------------------------------------------------------------------
+struct LogChf {
+  cd f, beta, d, e, c, N, G, H;
 };
 
-static ChfTerms chf_terms(const hexo_hparams& p, cd u, double tau) {
-  ChfTerms t;
-  t.xi = p.kappa + p.sigma * p.rho * I * u;
-  const cd fac = u * u - I * u;
-  t.d = std::sqrt(t.xi * t.xi + p.sigma * p.sigma * fac);
-  t.sinh_v = std::sinh(t.d * tau * .5);
-  t.cosh_v = std::cosh(t.d * tau * .5);
-  t.A1 = fac * t.sinh_v;
-  t.A2 = t.d / p.v_0 * t.cosh_v + t.xi / p.v_0 * t.sinh_v;
-  t.A = t.A1 / t.A2;
-  t.exp_kappa_tau = std::exp(p.kappa * tau * .5);
-  t.B = t.d * t.exp_kappa_tau / (p.v_0 * t.A2);
-  t.D = std::log((2. * t.d) / (t.d + t.xi + (t.d - t.xi) * std::exp(-t.d * tau))) +
-        (p.kappa - t.d) * tau * .5;
+static LogChf log_chf_parts(const hexo_hparams& p, cd u, double tau) {
+  LogChf t;
+  const cd s = -u;
+  t.f = s * s + I * s;
+  t.beta = p.kappa - p.rho * p.sigma * I * s;
+  t.d = std::sqrt(t.beta * t.beta + p.sigma * p.sigma * t.f);
+  t.e = std::exp(-t.d * tau);
+  t.c = t.beta - t.d;
+  t.N = t.d * (1. + t.e) + t.beta * (1. - t.e);
+  t.G = t.c * tau - 2. * std::log(t.N / (2. * t.d));
+  t.H = (1. - t.e) / t.N;
   return t;
 }
 
-// src/HDistribution.cpp:32-38
-static cd chf_value(const hexo_hparams& p, cd u, double tau, const ChfTerms& t) {
-  return std::exp((p.kappa * p.v_m * p.rho * tau * u * I) / p.sigma - t.A +
-                  (2. * t.D * p.kappa * p.v_m) / (p.sigma * p.sigma));
+static cd log_chf(const hexo_hparams& p, const LogChf& t) {
+  return p.kappa * p.v_m / (p.sigma * p.sigma) * t.G - p.v_0 * t.f * t.H;
 }
 
-// chf and its partial derivatives in HParams order (v_0, v_m, rho, kappa, sigma),
-// src/HDistribution.cpp:57-88
+static cd chf_value(const hexo_hparams& p, cd u, double tau) {
+  return std::exp(log_chf(p, log_chf_parts(p, u, tau)));
+}
+
+// chf and its partial derivatives in HParams order (v_0, v_m, rho, kappa, sigma)
 static void chf_and_grad(const hexo_hparams& p, cd u, double tau, cd out[6]) {
-  const ChfTerms t = chf_terms(p, u, tau);
-  const cd phi = chf_value(p, u, tau, t);
-  const cd iu = I * u, fac = u * u - iu;
-  const cd d_rho = t.xi * p.sigma * iu / t.d;
-  const cd A2_rho = p.sigma * iu * (2. + t.xi * tau) / (2. * t.d * p.v_0) *
-                    (t.xi * t.cosh_v + t.d * t.sinh_v);
-  const cd B_rho = t.exp_kappa_tau / p.v_0 * (d_rho / t.A2 - t.d / (t.A2 * t.A2) * A2_rho);
-  const cd A1_rho = (iu * fac * tau * t.xi * p.sigma) / (2. * t.d) * t.cosh_v;
-  const cd A_rho = A1_rho / t.A2 - t.A / t.A2 * A2_rho;
-  const cd B_kappa = -I / (p.sigma * u) * B_rho + t.B * tau * .5;
-  const cd d_sigma = (p.rho / p.sigma - 1. / t.xi) * d_rho + p.sigma * u * u / t.d;
-  const cd A1_sigma = fac * .5 * tau * d_sigma * t.cosh_v;
-  const cd A2_sigma = p.rho / p.sigma * A2_rho +
-                      (2. + tau * t.xi) / (p.v_0 * tau * t.xi * iu) * A1_rho +
-                      p.sigma * tau * t.A1 / p.v_0 * .5;
-  const cd A_sigma = A1_sigma / t.A2 - t.A / t.A2 * A2_sigma;
-  const cd tiu_vm_s = p.v_m * tau * iu / p.sigma;
-  const double s2 = p.sigma * p.sigma;
-  const double kvm2_s2 = 2. * p.kappa * p.v_m / s2;
-  const cd h_v0 = -t.A / p.v_0;
-  const cd h_vm = 2. * p.kappa / s2 * t.D + p.kappa * p.rho * tau * iu / p.sigma;
-  const cd h_sigma = -A_sigma - 2. * kvm2_s2 / p.sigma * t.D +
-                     kvm2_s2 / t.d * (d_sigma - t.d / t.A2 * A2_sigma) -
-                     tiu_vm_s / p.sigma * p.rho * p.kappa;
-  const cd h_kappa = -A_rho / (p.sigma * iu) + 2. * p.v_m / s2 * t.D + kvm2_s2 / t.B * B_kappa +
-                     tiu_vm_s * p.rho;
-  const cd h_rho = -A_rho + kvm2_s2 / t.d * (d_rho - t.d / t.A2 * A2_rho) + tiu_vm_s * p.kappa;
+  const LogChf t = log_chf_parts(p, u, tau);
+  const cd s = -u;
+  const double s2 = p.sigma * p.sigma, w = p.kappa * p.v_m / s2;
+  // derivative of ln chf along (beta', half of d(sigma^2 f)) -- without the explicit
+  // dependence of the prefactor kappa theta / sigma^2 on the parameter
+  auto along = [&](cd dbeta, cd half_ds2f) {
+    const cd dd = (t.beta * dbeta + half_ds2f) / t.d;
+    const cd dN = dd * (1. + t.e) + dbeta * (1. - t.e) + t.c * tau * t.e * dd;
+    const cd dG = (dbeta - dd) * tau - 2. * (dN / t.N - dd / t.d);
+    const cd dH = (tau * t.e * dd * t.N - (1. - t.e) * dN) / (t.N * t.N);
+    return w * dG - p.v_0 * t.f * dH;
+  };
+  const cd phi = std::exp(log_chf(p, t));
   out[0] = phi;
-  out[1] = phi * h_v0;
-  out[2] = phi * h_vm;
-  out[3] = phi * h_rho;
-  out[4] = phi * h_kappa;
-  out[5] = phi * h_sigma;
+  out[1] = phi * (-t.f * t.H);                                              // v_0
+  out[2] = phi * (p.kappa / s2 * t.G);                                      // v_m
+  out[3] = phi * along(-p.sigma * I * s, 0.);                               // rho
+  out[4] = phi * (p.v_m / s2 * t.G + along(1., 0.));                        // kappa
+  out[5] = phi * (-2. * w / p.sigma * t.G + along(-p.rho * I * s, p.sigma * t.f));  // sigma
 }
 
-// SWIFT truncation error bound for wavelet scale m, src/HDistribution.cpp:8-11
+// SWIFT truncation error bound for wavelet scale m (HDistribution::int_error,
+// src/HDistribution.cpp:8-11): |chf(2^m pi) + chf(-2^m pi)| / (4 2^m pi^2 tau).  For real u the
+// two values are complex conjugates, so the numerator is 2 |Re chf(2^m pi)|.
 static double truncation_error(const hexo_hparams& p, double tau, unsigned m) {
   const double e = std::exp2((double)m);
-  const cd a = chf_value(p, e * M_PI, tau, chf_terms(p, e * M_PI, tau));
-  const cd b = chf_value(p, -e * M_PI, tau, chf_terms(p, -e * M_PI, tau));
-  return std::abs(a + b) / (4 * e * M_PI * M_PI * tau);
+  return std::fabs(chf_value(p, e * M_PI, tau).real()) / (2 * e * M_PI * M_PI * tau);
 }
 
-// cumulants of the log-return, src/HDistribution.cpp:90-113
-static double cumulant1(const hexo_hparams& p, double tau) { return -.5 * p.v_m * tau; }
-static double cumulant2(const hexo_hparams& p, double t) {
-  const double s2 = p.v_m, r = p.rho, a = p.kappa, k = p.sigma;
-  const double a2 = a * a, a3 = a2 * a, k2 = k * k;
-  return s2 / (8 * a3) *
-         (-k2 * std::exp(-2 * a * t) + 4 * k * std::exp(-a * t) * (k - 2 * a * r) +
-          2 * a * t * (4 * a2 + k2 - 4 * a * k * r) + k * (8 * a * r - 3 * k));
-}
-static double cumulant4(const hexo_hparams& p, double t) {
-  const double s2 = p.v_m, r = p.rho, a = p.kappa, k = p.sigma;
-  const double a2 = a * a, a3 = a2 * a, a4 = a3 * a;
-  const double k2 = k * k, k3 = k2 * k, k4 = k3 * k;
-  const double t2 = t * t, r2 = r * r;
-  return (3 * k2 * s2) / (64 * std::pow(a, 7)) *
-         (-3 * k4 * std::exp(-4 * a * t) -
-          8 * k2 * std::exp(-3 * a * t) *
-              (2 * a * k * t * (k - 2 * a * r) + 4 * a2 + k2 - 6 * a * k * r) -
-          4 * std::exp(-2 * a * t) *
-              (4 * a2 * k2 * t2 * std::pow(k - 2 * a * r, 2) +
-               2 * a * k * t * (k3 - 16 * a3 * r - 12 * a * k2 * r + 4 * a2 * k * (3 + 4 * r2)) +
-               8 * a4 - 3 * k4 - 32 * a3 * k * r + 8 * a * k3 * r + 16 * a2 * k2 * r2) -
-          8 * std::exp(-a * t) *
-              (-2 * a2 * k * t2 * std::pow(k - 2 * a * r, 3) -
-               8 * a * t *
-                   (k4 - 7 * a * k3 * r + 4 * a4 * r2 - 8 * a3 * k * r * (1 + r2) +
-                    a2 * k2 * (3 + 14 * r2)) -
-               9 * k4 + 70 * a * k3 * r + 32 * a3 * k * r * (4 + 3 * r2) - 16 * a4 * (1 + 4 * r2) -
-               4 * a2 * k2 * (9 + 40 * r2)) +
-          4 * a * t *
-              (5 * k4 - 40 * a * k3 * r - 32 * a3 * k * r * (3 + 2 * r2) + 16 * a4 * (1 + 4 * r2) +
-               24 * a2 * k2 * (1 + 4 * r2)) -
-          73 * k4 + 544 * a * k3 * r + 128 * a3 * k * r * (7 + 6 * r2) - 32 * a4 * (3 + 16 * r2) -
-          64 * a2 * k2 * (4 + 19 * r2));
+// ---------------------------------------------------------------------------------------------
+// Cumulants of the log-return for the integration range (HDistribution::first/second/
+// fourth_order_moment, src/HDistribution.cpp:90-113, which print closed forms of the
+// stationary-start case v_0 = v_m).  Here they come out of the model instead of a formula sheet:
+// E[exp(w x)] = exp(A(t, w) + B(t, w) v_0) with  B' = sigma^2/2 B^2 + (rho sigma w - kappa) B
+// + (w^2 - w)/2,  A' = kappa theta B.  Expanding B = sum b_n w^n turns the Riccati equation into
+// the linear cascade
+//     b_n' = -kappa b_n + rho sigma b_{n-1} + sigma^2/2 sum_{j=1}^{n-1} b_j b_{n-j} + ([n=2]-[n=1])/2,
+// whose solutions are finite sums of t^k exp(-j kappa t).  ExpPoly holds such a sum exactly and
+// implements the three operations the cascade needs; cumulant n = n! (a_n + b_n v_m).
+// ---------------------------------------------------------------------------------------------
+struct ExpPoly {
+  static constexpr int J = 6, K = 6;  // exponents j kappa (j < J), powers t^k (k < K)
+  double c[J][K] = {};
+  double kappa = 0.0;
+  explicit ExpPoly(double kap) : kappa(kap) {}
+  double eval(double t) const {
+    double s = 0.0;
+    for (int j = 0; j < J; ++j) {
+      double poly = 0.0;
+      for (int k = K - 1; k >= 0; --k) poly = poly * t + c[j][k];
+      s += poly * std::exp(-j * kappa * t);
+    }
+    return s;
+  }
+  void axpy(double a, const ExpPoly& x) {
+    for (int j = 0; j < J; ++j)
+      for (int k = 0; k < K; ++k) c[j][k] += a * x.c[j][k];
+  }
+  ExpPoly times(const ExpPoly& x) const {
+    ExpPoly r(kappa);
+    for (int j = 0; j < J; ++j)
+      for (int k = 0; k < K; ++k)
+        if (c[j][k] != 0.0)
+          for (int j2 = 0; j + j2 < J; ++j2)
+            for (int k2 = 0; k + k2 < K; ++k2) r.c[j + j2][k + k2] += c[j][k] * x.c[j2][k2];
+    return r;
+  }
+  // exp(-lambda t) int_0^t exp(lambda s) g(s) ds with lambda = shift kappa: shift = 1 solves
+  // y' = -kappa y + g, y(0) = 0; shift = 0 is the plain integral
+  ExpPoly integrate(int shift) const {
+    ExpPoly r(kappa);
+    for (int j = 0; j < J; ++j)
+      for (int k = 0; k < K; ++k) {
+        const double g = c[j][k];
+        if (g == 0.0) continue;
+        const double alpha = (shift - j) * kappa;  // int s^k exp(alpha s) ds
+        if (shift == j) {
+          r.c[shift][k + 1] += g / (k + 1);
+          continue;
+        }
+        // exp(alpha s) sum_i (-1)^i k!/(k-i)! s^(k-i) / alpha^(i+1), between 0 and t
+        double fac = 1.0, pw = alpha;
+        for (int i = 0; i <= k; ++i) {
+          const double term = ((i & 1) ? -g : g) * fac / pw;
+          r.c[j][k - i] += term;               // upper limit: exp(alpha t) exp(-shift kappa t)
+          if (i == k) r.c[shift][0] -= term;   // lower limit: only the s^0 term survives at s = 0
+          fac *= (k - i);
+          pw *= alpha;
+        }
+      }
+    return r;
+  }
+};
+
+// cumulants 1, 2 and 4 of the log-return at time tau for v_0 = v_m
+static void cumulants_124(const hexo_hparams& p, double tau, double out[3]) {
+  const double kap = p.kappa, half_s2 = .5 * p.sigma * p.sigma, rs = p.rho * p.sigma;
+  std::vector<ExpPoly> b(5, ExpPoly(kap));
+  double cum[5] = {};
+  double fact = 1.0;
+  for (int n = 1; n <= 4; ++n) {
+    ExpPoly g(kap);  // right-hand side of b_n' + kappa b_n
+    if (n == 1) g.c[0][0] = -.5;
+    if (n == 2) g.c[0][0] = .5;
+    if (n > 1) g.axpy(rs, b[n - 1]);
+    for (int j = 1; j < n; ++j) g.axpy(half_s2, b[j].times(b[n - j]));
+    b[n] = g.integrate(1);
+    ExpPoly a = b[n].integrate(0);  // a_n / (kappa theta)
+    fact *= n;
+    cum[n] = fact * (kap * p.v_m * a.eval(tau) + p.v_m * b[n].eval(tau));
+  }
+  out[0] = cum[1];
+  out[1] = cum[2];
+  out[2] = cum[4];
 }
 
 // frequency of wavelet coefficient i, src/SWIFT.cpp:18-20
@@ -201,6 +257,12 @@ int hexo_heston_chf(const hexo_hparams* p, double tau, double u_re, double u_im,
   return HEXO_OK;
 }
 
+int hexo_heston_cumulants(const hexo_hparams* p, double tau, double out[3]) {
+  if (!p || !out || !(tau > 0) || !(p->kappa > 0)) return HEXO_ERR_INVALID_ARGUMENT;
+  cumulants_124(*p, tau, out);
+  return HEXO_OK;
+}
+
 // SwiftParameters(distr, S, chain), src/SWIFT.cpp:21-35.  truncation_precision: the reference
 // uses 1e-7 in its release build and 1e-10 in debug (SWIFT.cpp:12-16); <= 0 selects 1e-7.
 int hexo_swift_default_params(const hexo_hparams* p, double tau, double risk_free, double S,
@@ -214,8 +276,9 @@ int hexo_swift_default_params(const hexo_hparams* p, double tau, double risk_fre
   }
   const double hi = risk_free * tau + std::log(S / min_strike);
   const double lo = risk_free * tau + std::log(S / max_strike);
-  const double c = std::abs(cumulant1(*p, tau)) +
-                   10. * std::sqrt(std::fabs(cumulant2(*p, tau)) + std::sqrt(std::abs(cumulant4(*p, tau))));
+  double cum[3];
+  cumulants_124(*p, tau, cum);
+  const double c = std::fabs(cum[0]) + 10. * std::sqrt(std::fabs(cum[1]) + std::sqrt(std::fabs(cum[2])));
   out->m = m;
   out->exp2_m = (uint32_t)std::exp2((double)m);
   out->sqrt_exp2_m = std::sqrt((double)out->exp2_m);

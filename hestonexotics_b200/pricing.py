@@ -39,7 +39,9 @@ class HQEAnderson:
 
 
 _NORMAL_MODES = {"f32": _lib.NORMAL_F32, "as-built": _lib.NORMAL_F32, "f64": _lib.NORMAL_F64,
-                 _lib.NORMAL_F32: _lib.NORMAL_F32, _lib.NORMAL_F64: _lib.NORMAL_F64}
+                 "f32-ppnd7": _lib.NORMAL_F32_PPND7,
+                 _lib.NORMAL_F32: _lib.NORMAL_F32, _lib.NORMAL_F64: _lib.NORMAL_F64,
+                 _lib.NORMAL_F32_PPND7: _lib.NORMAL_F32_PPND7}
 _RNG_MODES = {"shishua": 0, "philox": 1, 0: 0, 1: 1}   # hexo_rng_mode
 _GRID_MODES = {"reference": 0, "exact": 1, 0: 0, 1: 1}  # hexo_schedule_mode
 _CV_MODES = {None: 0, "none": 0, "underlying": 1, 0: 0, 1: 1}  # hexo_control_variate
@@ -75,7 +77,7 @@ class _Request:
             # the reference trusts the caller (src/Main.cpp:53-57 computes it); be strict
             raise ValueError(f"n_opts={n_opts} but the chains hold {self.n_opts} options")
         if normal_mode not in _NORMAL_MODES:
-            raise ValueError(f"normal_mode must be 'f32' or 'f64', got {normal_mode!r}")
+            raise ValueError(f"normal_mode must be 'f32', 'f64' or 'f32-ppnd7', got {normal_mode!r}")
         if rng not in _RNG_MODES:
             raise ValueError(f"rng must be 'shishua' or 'philox', got {rng!r}")
         if time_grid not in _GRID_MODES:

@@ -22,6 +22,16 @@ def chf_chf_grad(p: HParams, tau: float, u: complex) -> np.ndarray:
     return out[0::2] + 1j * out[1::2]
 
 
+def cumulants(p: HParams, tau: float) -> np.ndarray:
+    """Cumulants 1, 2, 4 of the log-return for v_0 := v_m (HDistribution::first/second/
+    fourth_order_moment, src/HDistribution.cpp:90-113)."""
+    lib = _lib.load()
+    out = np.zeros(3)
+    hp = _lib.HexoHParams(*p.as_tuple())
+    _lib.check(lib.hexo_heston_cumulants(C.byref(hp), float(tau), out.ctypes.data_as(_lib.c_double_p)))
+    return out
+
+
 def swift_parameters(p: HParams, tau: float, risk_free: float, S: float, min_strike: float,
                      max_strike: float, truncation_precision: float = 0.0) -> _lib.HexoSwiftParams:
     """SwiftParameters(distr, S, chain), src/SWIFT.cpp:21-35."""

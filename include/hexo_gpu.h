@@ -50,7 +50,16 @@ typedef enum { HEXO_PAYOFF_ASIAN = 0, HEXO_PAYOFF_EUROPEAN = 1 } hexo_payoff;
  * BUILT: src/as241.f90:20-25 declares every local and coefficient default REAL
  * and nothing in Makefile.am promotes them.  F64 is the documented AS241
  * accuracy ("1 part in 10**16", as241.f90:4). */
-typedef enum { HEXO_NORMAL_F32 = 0, HEXO_NORMAL_F64 = 1 } hexo_normal_mode;
+/* F32_PPND7 (optional, faster): single precision with the coefficients of PPND7, the routine the
+ * same algorithm AS241 prescribes for single precision (degree 3/3 and 3/2 rational functions on
+ * the same regions).  Its values agree with the as-built reference within the tolerance stated
+ * for F32 (tests/test_normals_gpu.py).  Available for the default generator, drift and plain
+ * sums; other combinations are refused. */
+typedef enum {
+  HEXO_NORMAL_F32 = 0,
+  HEXO_NORMAL_F64 = 1,
+  HEXO_NORMAL_F32_PPND7 = 2
+} hexo_normal_mode;
 
 /* Generator of the u64 words.  SHISHUA is the reference's (src/RNG.cpp:24-29, stream s seeded
  * {seed,s,0,0}).  PHILOX is an optional counter-based mode that the reference does not have:
@@ -279,6 +288,10 @@ typedef struct {
  * chf and its partials in HParams order v_0, v_m, rho, kappa, sigma; risk-free rate is not
  * part of the reference's chf. */
 int hexo_heston_chf(const hexo_hparams *p, double tau, double u_re, double u_im, double out[12]);
+/* Cumulants 1, 2 and 4 of the log-return at time tau for a stationary start (v_0 := v_m), the
+ * quantities HDistribution::first/second/fourth_order_moment return (src/HDistribution.cpp:90-113)
+ * and SwiftParameters turns into the integration range (src/SWIFT.cpp:21-35). */
+int hexo_heston_cumulants(const hexo_hparams *p, double tau, double out[3]);
 
 /* SwiftParameters(distr, S, chain) (src/SWIFT.cpp:21-35); truncation_precision <= 0
  * selects the reference's release value 1e-7 (SWIFT.cpp:12-16). */

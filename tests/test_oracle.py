@@ -91,6 +91,32 @@ def test_ppnd16_hash_sums_product_table():
     assert sums == HASH_SUMS
 
 
+def test_ppnd7_hash_sums_product_table():
+    """The optional HEXO_NORMAL_F32_PPND7 mode uses AS241's single-precision routine PPND7; its
+    coefficients (csrc/normals.cuh) are checked against the hash sums Wichura's paper prints for
+    that routine (AB 32.3184577772, CD 15.7614929821), and numerically against the double
+    oracle: PPND7 claims "about 1 part in 10**7"."""
+    text = open(os.path.join(ROOT, "hestonexotics_b200", "csrc", "normals.cuh")).read()
+    body = text[text.index("struct Ppnd7 {"):]
+    body = body[:body.index("};")]
+    co = {k: Decimal(m) for k, m in re.findall(r"\b([A-D][0-3]) = ([0-9.]+)e[+-]\d+f", body)}
+    assert len(co) == 13
+    assert sum(v for k, v in co.items() if k[0] in "AB") == Decimal("32.3184577772")
+    assert sum(v for k, v in co.items() if k[0] in "CD") == Decimal("15.7614929821")
+    val = {k: float(x) for k, x in re.findall(r"\b([A-D][0-3]) = ([0-9.e+-]+)f", body)}
+    p = np.concatenate([np.linspace(1e-9, 0.5, 20001), 10.0 ** -np.linspace(2, 10.8, 2000)])
+    q = p - 0.5
+    r = 0.180625 - q * q
+    cen = q * (((val["A3"] * r + val["A2"]) * r + val["A1"]) * r + val["A0"]) / \
+        (((val["B3"] * r + val["B2"]) * r + val["B1"]) * r + 1.0)
+    rt = np.sqrt(-np.log(p)) - 1.6
+    tail = -(((val["C3"] * rt + val["C2"]) * rt + val["C1"]) * rt + val["C0"]) / \
+        ((val["D2"] * rt + val["D1"]) * rt + 1.0)
+    z = np.where(np.abs(q) <= 0.425, cen, tail)
+    ref = oa.ppnd16(p, oa.NORMAL_F64)
+    assert (np.abs(z - ref) / np.maximum(1.0, np.abs(ref))).max() < 3e-7
+
+
 def test_ppnd16_f64_vs_ndtri():
     rng = np.random.default_rng(7)
     p = np.concatenate([rng.random(20000), 10.0 ** -rng.uniform(3, 300, 2000),

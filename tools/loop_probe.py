@@ -1,5 +1,7 @@
 """Development probe: throughput of the FP64 step loop alone (HEXO_NO_REFILL=1) and of the full
-kernel at different numbers of warps per SM (block size x blocks)."""
+kernel at different numbers of warps per SM (block size x blocks).  Needs the development build
+of the library (python -m hestonexotics_b200.build --dev; HEXO_GPU_LIB=.../libhexo_gpu_dev.so):
+the shipped library ignores these environment variables."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import hestonexotics_b200 as hx
@@ -8,9 +10,9 @@ lib = _lib.load(); _lib.check(lib.hexo_gpu_init(0))
 p = hx.HParams(0.04, 0.04, -0.7, 2.0, 0.5)
 A = hx.HQEAnderson(hx.AAsianCallNonAdaptive)
 ch = [hx.OptionsChain.from_strikes(1.0, [100.0])]
-for norefill in ("1", "0"):
+for norefill in ("0", "1", "2"):
     os.environ["HEXO_NO_REFILL"] = norefill
-    for blk, nblk in ((32, 4), (64, 4), (128, 4), (256, 2), (64, 8), (128, 2), (32, 8)):
+    for blk, nblk in ((256, 2), (128, 2)):
         os.environ["HEXO_BLOCK"] = str(blk)
         ns = 148 * nblk * blk
         n = ns * 16
