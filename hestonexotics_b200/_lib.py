@@ -26,7 +26,8 @@ ABI_SYMBOLS = (
     "hexo_gpu_normals_from_words",
 )
 # host-only semi-analytic benchmark functions of the same library (no hexo_gpu_ prefix)
-HOST_SYMBOLS = ("hexo_heston_chf", "hexo_heston_cumulants", "hexo_swift_default_params",
+HOST_SYMBOLS = ("hexo_heston_chf", "hexo_heston_cumulants", "hexo_heston_geometric_asian",
+                "hexo_swift_default_params",
                 "hexo_swift_price_chain")
 
 HEXO_OK = 0
@@ -135,6 +136,7 @@ def load() -> C.CDLL:
     lib.hexo_gpu_measure_fp64_peak.argtypes = [c_double_p, C.POINTER(C.c_float)]
     lib.hexo_heston_chf.argtypes = [C.POINTER(HexoHParams), C.c_double, C.c_double, C.c_double,
                                     c_double_p]
+    lib.hexo_heston_geometric_asian.argtypes = [C.POINTER(HexoPriceRequest), c_double_p]
     lib.hexo_heston_cumulants.argtypes = [C.POINTER(HexoHParams), C.c_double, c_double_p]
     lib.hexo_swift_default_params.argtypes = [C.POINTER(HexoHParams), C.c_double, C.c_double,
                                               C.c_double, C.c_double, C.c_double, C.c_double,

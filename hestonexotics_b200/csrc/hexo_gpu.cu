@@ -32,6 +32,7 @@
 #include <vector>
 
 #include "../../include/hexo_gpu.h"
+#include "host_internal.h"
 #include "path_kernels.h"
 
 namespace hexo {
@@ -370,8 +371,13 @@ static int check_request(const hexo_price_request* r, bool need_strikes) {
     return fail(HEXO_ERR_INVALID_ARGUMENT, "unknown rng_mode %d", r->rng_mode);
   if (r->schedule_mode != HEXO_SCHEDULE_REFERENCE && r->schedule_mode != HEXO_SCHEDULE_EXACT)
     return fail(HEXO_ERR_INVALID_ARGUMENT, "unknown schedule_mode %d", r->schedule_mode);
-  if (r->control_variate != HEXO_CV_NONE && r->control_variate != HEXO_CV_UNDERLYING)
+  if (r->control_variate != HEXO_CV_NONE && r->control_variate != HEXO_CV_UNDERLYING &&
+      r->control_variate != HEXO_CV_GEOMETRIC)
     return fail(HEXO_ERR_INVALID_ARGUMENT, "unknown control_variate %d", r->control_variate);
+  if (r->control_variate == HEXO_CV_GEOMETRIC &&
+      (r->payoff != HEXO_PAYOFF_ASIAN || r->rng_mode != HEXO_RNG_SHISHUA))
+    return fail(HEXO_ERR_INVALID_ARGUMENT,
+                "HEXO_CV_GEOMETRIC is the control of the Asian payoff (shishua generator)");
   if (r->drift_mode != HEXO_DRIFT_REFERENCE && r->drift_mode != HEXO_DRIFT_MARTINGALE)
     return fail(HEXO_ERR_INVALID_ARGUMENT, "unknown drift_mode %d", r->drift_mode);
   // The reference divides by kappa and sigma (HSimulation.tpp:60,75-77) and takes log(S) (:90);
@@ -459,6 +465,18 @@ static int build_segments(const hexo_price_request* r, bool with_strikes,
     g.n_strikes = with_strikes ? r->strike_offsets[k + 1] - r->strike_offsets[k] : 0;
     g.pad = 0;
   }
+  {  // sum of the Asian policy's trapezoid weights per expiry (see control_means)
+    double weight = 0.0;
+    for (uint32_t k = 0; k < r->n_chains; ++k) {
+      SegConst& g = out[k];
+      if (g.n_steps > 0) {
+        if (k > 0) weight += 2.0 * g.hcarry;
+        weight += g.h * (double)(g.n_steps - 1);
+      }
+      const double w = weight + 2.0 * g.hs;
+      g.inv_logw = w > 0.0 ? 1.0 / w : 0.0;
+    }
+  }
   if (steps_per_path) *steps_per_path = total;
   return HEXO_OK;
 }
@@ -467,6 +485,7 @@ static int build_segments(const hexo_price_request* r, bool with_strikes,
 // [sum pf c] per option and [sum c | sum c^2] per maturity
 static size_t sums_len(const hexo_price_request* r) {
   const size_t n_opts = r->strike_offsets[r->n_chains];
+  if (r->control_variate == HEXO_CV_GEOMETRIC) return 5 * n_opts;
   return r->control_variate ? 3 * n_opts + 2 * (size_t)r->n_chains : 2 * n_opts;
 }
 
@@ -481,14 +500,10 @@ static void control_means(const hexo_price_request* r, const std::vector<SegCons
                           std::vector<double>& ec) {
   ec.assign(r->n_chains, 0.0);
   if (r->payoff != HEXO_PAYOFF_ASIAN) return;
-  double weight = 0.0;  // sum of trapezoid weights accumulated in `integral` (path kernel)
   for (uint32_t k = 0; k < r->n_chains; ++k) {
-    const SegConst& g = segs[k];
-    if (g.n_steps > 0) {
-      if (k > 0) weight += 2.0 * g.hcarry;      // trapezoid of the step that crossed expiry k-1
-      weight += g.h * (double)(g.n_steps - 1);  // all but the crossing step of this segment
-    }
-    ec[k] = r->S * ((weight + 2.0 * g.hs) / g.expiry - 1.0);  // dx * w has mean zero
+    const SegConst& g = segs[k];  // inv_logw = 1 / (sum of the weights), build_segments
+    if (!(g.inv_logw > 0.0)) continue;
+    ec[k] = r->S * (1.0 / (g.inv_logw * g.expiry) - 1.0);  // dx * w has mean zero
   }
 }
 
@@ -499,13 +514,38 @@ static void control_means(const hexo_price_request* r, const std::vector<SegCons
 static int finish_prices(const hexo_price_request* r, const double* sums, double* prices,
                          double* se) {
   std::vector<double> ec(r->n_chains, 0.0);
+  const uint32_t n_opts = r->strike_offsets[r->n_chains];
   if (r->control_variate) {
     std::vector<SegConst> segs;
     const int rc = build_segments(r, true, segs, nullptr);
     if (rc) return rc;
+    if (r->control_variate == HEXO_CV_GEOMETRIC) {
+      // per-option control c_j = max(G - K_j, 0) with its semi-analytic mean (geo_asian_host.cu);
+      // sums = [pf | pf^2 | pf c | c | c^2], n_opts each
+      std::vector<double> eg;
+      const int rg = geometric_asian_means(r, segs, eg);
+      if (rg) return rg;
+      const double n = (double)r->n_paths;
+      const double *sp = sums, *sq = sums + n_opts, *sx = sums + 2 * (size_t)n_opts,
+                   *sc = sums + 3 * (size_t)n_opts, *sc2 = sums + 4 * (size_t)n_opts;
+      for (uint32_t j = 0; j < n_opts; ++j) {
+        const double mean = sp[j] / n, mean_c = sc[j] / n;
+        double var = n > 1 ? std::max(0.0, (sq[j] - n * mean * mean) / (n - 1)) : 0.0;
+        const double var_c = n > 1 ? std::max(0.0, (sc2[j] - n * mean_c * mean_c) / (n - 1)) : 0.0;
+        double price = mean;
+        if (var_c > 0.0) {
+          const double cov = (sx[j] - n * mean * mean_c) / (n - 1);
+          const double beta = cov / var_c;
+          price = mean - beta * (mean_c - eg[j]);
+          var = std::max(0.0, var - beta * cov);
+        }
+        prices[j] = price;
+        if (se) se[j] = sqrt(var / n);
+      }
+      return HEXO_OK;
+    }
     control_means(r, segs, ec);
   }
-  const uint32_t n_opts = r->strike_offsets[r->n_chains];
   const double n = (double)r->n_paths;
   const double* sp = sums;
   const double* sq = sums + n_opts;
@@ -546,17 +586,18 @@ struct Plan {
   void* blob = nullptr;       // [segs | strikes | partials | sums]
   double* sums_dev = nullptr; // inside blob unless caller-supplied
   size_t gacc_bytes = 0;
-  bool cv = false;  // control-variate sums (template parameter CV of the path kernel)
+  int cv = 0;  // hexo_control_variate (template parameter CV of the path kernel)
   bool mart = false;  // HEXO_DRIFT_MARTINGALE (template parameter MART)
 };
 
 // The path-kernel instantiations live in their own translation units (path_kernels_*.cu), which
 // build in parallel; path_kernels.h declares the selectors.
 static PathKernel pick_kernel(int payoff, int normal_mode, uint32_t n_seg, int rng_mode = 0,
-                              bool cv = false, bool mart = false) {
+                              int cv = 0, bool mart = false) {
   const int segs = n_seg == 1                       ? kSegsSingle
                    : n_seg <= (uint32_t)kInlineSegs ? kSegsInline
                                                     : kSegsGlobal;
+  if (cv == HEXO_CV_GEOMETRIC) return path_kernel_shishua_geo(normal_mode, segs, mart);
   if (mart)
     return rng_mode == HEXO_RNG_PHILOX ? path_kernel_philox_mart(payoff, normal_mode, segs, cv)
                                        : path_kernel_shishua_mart(payoff, normal_mode, segs, cv);
@@ -663,7 +704,7 @@ static int plan_fill(const hexo_price_request* r, uint64_t stream_begin, uint64_
   a.rem_streams = r->n_paths % r->n_streams;
   a.n_seg = r->n_chains;
   a.n_opts = n_opts;
-  p->cv = r->control_variate != HEXO_CV_NONE;
+  p->cv = r->control_variate;
   p->mart = r->drift_mode == HEXO_DRIFT_MARTINGALE;
   a.segs = reinterpret_cast<const SegConst*>(base);
   for (size_t k = 0; k < segs.size() && k < (size_t)kInlineSegs; ++k) a.seg_inline[k] = segs[k];
@@ -713,6 +754,10 @@ static void fill_stats(const Plan& p, float ms, hexo_gpu_stats* s) {
   s->smem_bytes = p.smem;
   s->kernel_launches = 2;
   s->kernel_ms = ms;
+}
+
+int build_request_segments(const hexo_price_request* r, std::vector<SegConst>& segs) {
+  return build_segments(r, true, segs, nullptr);
 }
 
 }  // namespace hexo
@@ -878,6 +923,22 @@ int hexo_gpu_price(const hexo_price_request* req, double* prices_out, double* st
 size_t hexo_gpu_sums_len(const hexo_price_request* req) {
   if (!req || !req->strike_offsets || req->n_chains == 0) return 0;
   return sums_len(req);
+}
+
+int hexo_heston_geometric_asian(const hexo_price_request* req, double* means_out) {
+  int rc = check_request(req, true);
+  if (rc) return rc;
+  if (!means_out) return fail(HEXO_ERR_INVALID_ARGUMENT, "means_out is NULL");
+  if (req->payoff != HEXO_PAYOFF_ASIAN)
+    return fail(HEXO_ERR_INVALID_ARGUMENT, "the geometric average belongs to the Asian payoff");
+  std::vector<SegConst> segs;
+  rc = build_segments(req, true, segs, nullptr);
+  if (rc) return rc;
+  std::vector<double> eg;
+  rc = geometric_asian_means(req, segs, eg);
+  if (rc) return rc;
+  for (size_t j = 0; j < eg.size(); ++j) means_out[j] = eg[j];
+  return HEXO_OK;
 }
 
 int hexo_gpu_finish(const hexo_price_request* req, const double* sums, double* prices_out,

@@ -406,6 +406,37 @@ __device__ __forceinline__ void accumulate_with_control(const double* fvbuf, uns
   }
 }
 
+// The same walk with the geometric-Asian control: per strike the payoff of the geometric average
+// c = max(G - K, 0) next to the payoff of the arithmetic one, and their sums
+// [sum pf | sum pf^2 | sum pf c | sum c | sum c^2].
+__device__ __forceinline__ void accumulate_with_geometric(const double* fvbuf, const double* gbuf,
+                                                          unsigned amask, int lane,
+                                                          const double* strikes, uint32_t n_strikes,
+                                                          double* sum, double* sq, double* cross,
+                                                          double* csum, double* csq) {
+  for (uint32_t j = lane; j < n_strikes; j += 32) {
+    const double K = __ldg(strikes + j);
+    double s = 0.0, q = 0.0, x = 0.0, c1 = 0.0, c2 = 0.0;
+#pragma unroll 4
+    for (int l = 0; l < 32; ++l) {
+      if ((amask >> l) & 1u) {
+        const double pf = fmax(fvbuf[l] - K, 0.0);
+        const double cg = fmax(gbuf[l] - K, 0.0);
+        s += pf;
+        q = fma(pf, pf, q);
+        x = fma(pf, cg, x);
+        c1 += cg;
+        c2 = fma(cg, cg, c2);
+      }
+    }
+    sum[j] += s;
+    sq[j] += q;
+    cross[j] += x;
+    csum[j] += c1;
+    csq[j] += c2;
+  }
+}
+
 // Where the per-maturity constants are read from: global memory (any number of maturities), the
 // kernel parameter bank indexed by the maturity (up to kInlineSegs), or -- one maturity, the
 // benchmark shape -- fixed parameter-bank addresses, which the compiler can keep in uniform
@@ -413,7 +444,9 @@ __device__ __forceinline__ void accumulate_with_control(const double* fvbuf, uns
 // then reads at most two register pairs.
 enum : int { kSegsGlobal = 0, kSegsInline = 1, kSegsSingle = 2 };
 
-template <int PAYOFF, int NORMAL_MODE, int SEGS, class Gen = Shishua, bool CV = false,
+// CV: hexo_control_variate -- 0 plain sums; 1 the control c = final value - S; 2 (Asian) the
+// geometric-Asian control c_j = max(G - K_j, 0), G = exp of the same accumulation applied to ln X
+template <int PAYOFF, int NORMAL_MODE, int SEGS, class Gen = Shishua, int CV = 0,
           bool MART = false>
 __global__ void __launch_bounds__(kMaxBlock, kMinBlocksPerSM)
 heston_qe_paths_kernel(const __grid_constant__ PathArgs a) {
@@ -443,7 +476,7 @@ heston_qe_paths_kernel(const __grid_constant__ PathArgs a) {
   sp += (size_t)32 * 8 * nwarps;
   const uint32_t tlist = pin32(smem_addr(sp) + kTailListBytes * warp);
   sp += (size_t)kTailListBytes * nwarps;
-#define HEXO_N_ACC (CV ? 3 * a.n_opts + 2 * a.n_seg : 2 * a.n_opts)
+#define HEXO_N_ACC (CV == 2 ? 5 * a.n_opts : CV ? 3 * a.n_opts + 2 * a.n_seg : 2 * a.n_opts)
   // The plain case spells its offsets out as the 64-bit product chain it has always been: the
   // register allocation of the whole kernel (114 registers, 1 % faster step loop) hangs on it.
   double* acc_all = a.gacc ? a.gacc + (CV ? (size_t)blockIdx.x * nwarps * HEXO_N_ACC
@@ -453,7 +486,11 @@ heston_qe_paths_kernel(const __grid_constant__ PathArgs a) {
       acc_all + (CV ? (size_t)warp * HEXO_N_ACC : (size_t)warp * 2 * a.n_opts);
   double* my_sq = my_sum + a.n_opts;
   double* my_cross = my_sq + a.n_opts;    // cv only: sum pf c per option ...
-  double* my_ctl = my_cross + a.n_opts;   // ... and sum c, sum c^2 per maturity (lane 0)
+  double* my_ctl = my_cross + a.n_opts;   // ... and sum c, sum c^2 per maturity (lane 0); with
+                                          // the geometric control per option: [n_opts | n_opts]
+  constexpr bool kGeo = kAsian && CV == 2;
+  // the warp's geometric averages at a maturity share the tail list's storage (idle then)
+  double* gbuf = reinterpret_cast<double*>(smem_raw + (tlist - smem_addr(smem_raw)));
   if (!a.gacc)
     for (uint32_t j = lane; j < HEXO_N_ACC; j += 32) my_sum[j] = 0.0;
   exp_table_init(exptab, tid, T);
@@ -488,6 +525,8 @@ heston_qe_paths_kernel(const __grid_constant__ PathArgs a) {
     // HQEAnderson::operator=(initial_state), HSimulation.tpp:26,87-94
     double V = a.v0, lnX = a.lnS, X = a.S, Xprev = a.S;
     double integral = 0.0;  // AAsianCallNonAdaptive::accumulated_value, reset per path (:34)
+    // geometric control: the same bookkeeping for L = ln X (lnX itself; Lprev, integralL)
+    double Lprev = a.lnS, integralL = 0.0;
     for (uint32_t k = 0; k < (SEGS == kSegsSingle ? 1u : a.n_seg); ++k) {
       SegConst g = SEGS == kSegsSingle   ? a.seg_inline[0]
                    : SEGS == kSegsInline ? a.seg_inline[k]
@@ -505,9 +544,10 @@ heston_qe_paths_kernel(const __grid_constant__ PathArgs a) {
           // AFTER update_earliest switched the step size (HSimulation.tpp:42-44),
           // i.e. with this segment's h.
           integral += g.hcarry * (X + Xprev);
+          if (kGeo) integralL += g.hcarry * (lnX + Lprev);
         }
-        const double Xa = X;
-        double sumX = 0.0;
+        const double Xa = X, La = lnX;
+        double sumX = 0.0, sumL = 0.0;
         // log-spot half of a step.  Asian: the spot itself is advanced multiplicatively
         // (X is needed every step, ln X never); European: ln X is accumulated and X = exp(ln X)
         // only where with_x says so (HSimulation.tpp:80-82)
@@ -521,6 +561,11 @@ heston_qe_paths_kernel(const __grid_constant__ PathArgs a) {
             if (keep_prev) Xprev = X;
             X = grow_spot(X, delta, exptab_s);
             sumX += X;
+            if (kGeo) {
+              if (keep_prev) Lprev = lnX;
+              lnX += delta;
+              sumL += lnX;
+            }
           } else {
             lnX += delta;
             if (decltype(with_x)::value) {
@@ -608,6 +653,10 @@ heston_qe_paths_kernel(const __grid_constant__ PathArgs a) {
                 }
                 X = Xn;
                 sumX += X;
+                if (kGeo) {
+                  lnX += delta;
+                  sumL += lnX;
+                }
               } else {
                 lnX += delta;
                 if (decltype(with_x)::value) {
@@ -631,6 +680,7 @@ heston_qe_paths_kernel(const __grid_constant__ PathArgs a) {
           // trapezoids of all but the crossing step: h/2 sum_{j<n} (X_j + X_{j-1}),
           // AsianContract.h:25-28; sumX includes the crossing step's X, take it out
           if (n > 0) integral += g.h * 0.5 * (Xa - Xprev + 2.0 * (sumX - X));
+          if (kGeo && n > 0) integralL += g.h * 0.5 * (La - Lprev + 2.0 * (sumL - lnX));
         } else {
           // European: X is only read at the expiry, so only the last two steps need it
           if (n > 2) run(n - 2, std::false_type{});
@@ -643,6 +693,9 @@ heston_qe_paths_kernel(const __grid_constant__ PathArgs a) {
           kAsian ? (integral + dx * g.w + g.hs * (X + Xprev)) / g.expiry : Xprev + dx * g.w;
       __syncwarp();
       fvbuf[lane] = fv;
+      if (kGeo)  // geometric average on the arithmetic average's own weights, normalised
+        gbuf[lane] = fast_exp(
+            (integralL + (lnX - Lprev) * g.w + g.hs * (lnX + Lprev)) * g.inv_logw, exptab_s);
       const unsigned amask = __ballot_sync(0xffffffffu, active);
       __syncwarp();
       // final_payoff for every strike of this chain (HSimulation.tpp:39-40): lane
@@ -662,6 +715,11 @@ heston_qe_paths_kernel(const __grid_constant__ PathArgs a) {
           my_sum[g.first_opt + j] += s;
           my_sq[g.first_opt + j] += q;
         }
+      } else if (CV == 2) {
+        accumulate_with_geometric(fvbuf, gbuf, amask, lane, a.strikes + g.first_opt, g.n_strikes,
+                                  my_sum + g.first_opt, my_sq + g.first_opt,
+                                  my_cross + g.first_opt, my_ctl + g.first_opt,
+                                  my_ctl + a.n_opts + g.first_opt);
       } else {
         accumulate_with_control(fvbuf, amask, lane, a.strikes + g.first_opt, g.n_strikes, a.S,
                                 my_sum + g.first_opt, my_sq + g.first_opt, my_cross + g.first_opt,

@@ -13,6 +13,8 @@ typedef void (*PathKernel)(const PathArgs);
 // payoff: hexo_payoff, normal_mode: hexo_normal_mode, segs: kSegsGlobal / kSegsInline / kSegsSingle
 PathKernel path_kernel_shishua(int payoff, int normal_mode, int segs);     // the default
 PathKernel path_kernel_shishua_ppnd7(int payoff, int segs);  // HEXO_NORMAL_F32_PPND7, plain sums
+// HEXO_CV_GEOMETRIC (Asian payoff): shishua generator; mart selects HEXO_DRIFT_MARTINGALE
+PathKernel path_kernel_shishua_geo(int normal_mode, int segs, bool mart);
 PathKernel path_kernel_shishua_cv(int payoff, int normal_mode, int segs);  // + control variate
 PathKernel path_kernel_philox(int payoff, int normal_mode, int segs, bool cv);
 // HEXO_DRIFT_MARTINGALE (path_kernels_*_mart*.cu)
@@ -25,7 +27,7 @@ PathKernel path_kernel_philox_mart(int payoff, int normal_mode, int segs, bool c
 // (the default family); 2 = single-maturity + device memory; 1 = device memory only (the optional
 // Philox families).  In the step loop the parameter-bank and device-memory variants are the
 // same code -- both pin the constants in registers.
-template <class Gen, bool CV, bool MART = false, int VARIANTS = 3>
+template <class Gen, int CV, bool MART = false, int VARIANTS = 3>
 inline PathKernel select_path_kernel(int payoff, int normal_mode, int segs) {
   constexpr int kOne = VARIANTS >= 2 ? kSegsSingle : kSegsGlobal;
   constexpr int kFew = VARIANTS >= 3 ? kSegsInline : kSegsGlobal;

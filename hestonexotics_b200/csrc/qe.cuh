@@ -42,6 +42,10 @@ struct SegConst {
   // HEXO_DRIFT_MARTINGALE only: A = K2 + K4/2 and its double, and -K3/2, the factor of V that
   // is left of K1 V once K0* = -ln M - (K1 + K3/2) V takes the place of K0
   double A, A2, K1m;
+  // HEXO_CV_GEOMETRIC only: 1 / (sum of the trapezoid weights applied up to this expiry), which
+  // normalises the geometric average (the weights sum to T except on the reference grid when the
+  // steps land on the expiry, SURVEY finding 6)
+  double inv_logw;
   uint32_t n_steps, first_opt, n_strikes, pad;
 };
 

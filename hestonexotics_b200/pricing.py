@@ -44,7 +44,7 @@ _NORMAL_MODES = {"f32": _lib.NORMAL_F32, "as-built": _lib.NORMAL_F32, "f64": _li
                  _lib.NORMAL_F32_PPND7: _lib.NORMAL_F32_PPND7}
 _RNG_MODES = {"shishua": 0, "philox": 1, 0: 0, 1: 1}   # hexo_rng_mode
 _GRID_MODES = {"reference": 0, "exact": 1, 0: 0, 1: 1}  # hexo_schedule_mode
-_CV_MODES = {None: 0, "none": 0, "underlying": 1, 0: 0, 1: 1}  # hexo_control_variate
+_CV_MODES = {None: 0, "none": 0, "underlying": 1, "geometric": 2, 0: 0, 1: 1, 2: 2}  # hexo_control_variate
 _DRIFT_MODES = {"reference": 0, "martingale": 1, 0: 0, 1: 1}  # hexo_drift_mode
 
 
@@ -83,7 +83,8 @@ class _Request:
         if time_grid not in _GRID_MODES:
             raise ValueError(f"time_grid must be 'reference' or 'exact', got {time_grid!r}")
         if control_variate not in _CV_MODES:
-            raise ValueError(f"control_variate must be None or 'underlying', got {control_variate!r}")
+            raise ValueError("control_variate must be None, 'underlying' or 'geometric', got "
+                             f"{control_variate!r}")
         if drift not in _DRIFT_MODES:
             raise ValueError(f"drift must be 'reference' or 'martingale', got {drift!r}")
         self.req = _lib.HexoPriceRequest(
@@ -94,8 +95,9 @@ class _Request:
             int(n_simulations), int(steps), int(seed), _NORMAL_MODES[normal_mode],
             _RNG_MODES[rng], int(n_streams), _GRID_MODES[time_grid], _CV_MODES[control_variate],
             _DRIFT_MODES[drift])
-        self.n_sums = 3 * self.n_opts + 2 * len(self.expiries) if self.req.control_variate \
-            else 2 * self.n_opts
+        cv = self.req.control_variate
+        self.n_sums = 5 * self.n_opts if cv == 2 else \
+            3 * self.n_opts + 2 * len(self.expiries) if cv else 2 * self.n_opts
 
 
 def _finish(rq: "_Request", sums: np.ndarray):
@@ -110,6 +112,18 @@ def _finish(rq: "_Request", sums: np.ndarray):
                                    prices.ctypes.data_as(_lib.c_double_p),
                                    se.ctypes.data_as(_lib.c_double_p)))
     return prices, se
+
+
+def geometric_asian_means(p: HParams, S: float, all_chains: Sequence[OptionsChain], steps: int,
+                          time_grid="reference") -> np.ndarray:
+    """E max(G - K, 0) per option: the discretely monitored geometric-Asian call under Heston at
+    r = 0 on the time grid of a price<>() call (hexo_heston_geometric_asian; host only)."""
+    lib = _lib.load()
+    rq = _Request(AAsianCallNonAdaptive, p, S, all_chains, 1, None, steps, 1, "f32", 1,
+                  time_grid=time_grid, control_variate="geometric")
+    out = np.zeros(rq.n_opts)
+    _lib.check(lib.hexo_heston_geometric_asian(C.byref(rq.req), out.ctypes.data_as(_lib.c_double_p)))
+    return out
 
 
 def price_full(scheme, p: HParams, S: float, all_chains: Sequence[OptionsChain],

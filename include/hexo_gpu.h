@@ -83,7 +83,19 @@ typedef enum { HEXO_SCHEDULE_REFERENCE = 0, HEXO_SCHEDULE_EXACT = 1 } hexo_sched
  * beta = cov(payoff, c) / var(c) estimated from the same paths; the standard error shrinks by
  * sqrt(1 - corr(payoff, c)^2).  The sums gain [sum payoff c] per option and [sum c | sum c^2]
  * per maturity (hexo_gpu_sums_len). */
-typedef enum { HEXO_CV_NONE = 0, HEXO_CV_UNDERLYING = 1 } hexo_control_variate;
+/* GEOMETRIC (Asian payoff) is the control the reference names: next to the arithmetic average
+ * A = sum w_i X_i / T the kernel accumulates Y = sum w_i ln X_i / sum w_i with the same weights
+ * (including the reference grid's last-step rule) and uses, per option, c_j = max(exp(Y) - K_j, 0).
+ * E[c_j] is the price of the discretely monitored geometric-Asian call under Heston at r = 0,
+ * evaluated on the host from the affine transform of ln X at the grid dates and one Fourier
+ * integral (hexo_heston_geometric_asian).  That mean belongs to the exact process, the simulation
+ * to its QE discretisation: the estimator also removes the part of the discretisation error the
+ * two payoffs share.  Sums: [sum pf | sum pf^2 | sum pf c | sum c | sum c^2], n_opts each. */
+typedef enum {
+  HEXO_CV_NONE = 0,
+  HEXO_CV_UNDERLYING = 1,
+  HEXO_CV_GEOMETRIC = 2
+} hexo_control_variate;
 
 /* Drift of the log-spot step.  REFERENCE is the reference's (HSimulation.tpp:75-80): the constant
  * K0 of Andersen's scheme, under which the simulated spot is only approximately a martingale
@@ -186,12 +198,17 @@ int hexo_gpu_price_batch(const hexo_price_request *reqs, uint32_t n_reqs, uint32
                          double *prices_out, double *stderr_out, hexo_gpu_stats *stats);
 
 /* Number of doubles a shard's sums hold for this request: 2 n_opts ([sum payoff | sum payoff^2]),
- * or 3 n_opts + 2 n_chains with a control variate ([.. | sum payoff c | sum c | sum c^2]).
+ * 3 n_opts + 2 n_chains with HEXO_CV_UNDERLYING ([.. | sum payoff c | sum c | sum c^2]), 5 n_opts
+ * with HEXO_CV_GEOMETRIC.
  * Sums of disjoint stream ranges add up; hexo_gpu_finish turns the total into prices and
  * standard errors exactly as hexo_gpu_price does (host only, no GPU). */
 size_t hexo_gpu_sums_len(const hexo_price_request *req);
 int hexo_gpu_finish(const hexo_price_request *req, const double *sums, double *prices_out,
                     double *stderr_out);
+/* Known means of the geometric-Asian control (HEXO_CV_GEOMETRIC): means_out[j] =
+ * E max(G - K_j, 0) for every option of an Asian request, G the geometric average on the
+ * request's time grid.  Host only, no GPU. */
+int hexo_heston_geometric_asian(const hexo_price_request *req, double *means_out);
 
 /* The same call spread over the first n_gpus devices of this process (n_gpus <= 0: all
  * visible devices): the single-process counterpart of the one-rank-per-GPU path, for callers

@@ -312,12 +312,18 @@ static void tapesrc_end(draw_src *d) { ((tape_ctx *)d->ctx)->step++; }
 /* src/inc/SDE.h:9-14 + the stepper's private log_X (HSimulation.h:23) */
 typedef struct {
   double cur_X, cur_V, prev_X, prev_V, cur_time, prev_time, log_X;
+  double prev_log_X; /* NOT in the reference: log_X before the step (geometric control variate) */
 } sde_state;
 
 /* AsianContract.h:15-18 / VanillaContract.h:15-17 */
 typedef struct {
   int payoff;
   double accumulated_value, final_value, earliest_unpriced_expi, init_step_size;
+  /* NOT in the reference (which only suggests a control variate, src/inc/HSimulation.h:51): the
+   * same accumulation applied to ln X instead of X -- the log of the geometric average with the
+   * arithmetic average's own weights (include/hexo_gpu.h, HEXO_CV_GEOMETRIC) */
+  double accumulated_log, final_log;
+  double accumulated_weight; /* sum of the trapezoid weights applied so far: normalises final_log */
 } policy;
 
 /* AsianContract.h:35-38, VanillaContract.h:32-35 */
@@ -330,12 +336,18 @@ static void policy_reset(policy *o) {
   if (o->payoff == ORACLE_ASIAN) {
     o->accumulated_value = 0.0;
     o->final_value = 0.0;
+    o->accumulated_log = 0.0;
+    o->final_log = 0.0;
+    o->accumulated_weight = 0.0;
   }
 }
 /* AsianContract.h:25-28 (European: empty, VanillaContract.h:24-26) */
 static void accumulate_value(policy *o, const sde_state *s) {
-  if (o->payoff == ORACLE_ASIAN)
+  if (o->payoff == ORACLE_ASIAN) {
     o->accumulated_value += o->init_step_size * .5 * (s->cur_X + s->prev_X);
+    o->accumulated_log += o->init_step_size * .5 * (s->log_X + s->prev_log_X);
+    o->accumulated_weight += o->init_step_size;
+  }
 }
 /* AsianContract.h:29-34 / VanillaContract.h:28-31 */
 static void accumulate_final_value(policy *o, const sde_state *s) {
@@ -343,6 +355,10 @@ static void accumulate_final_value(policy *o, const sde_state *s) {
     double step_interpolation =
         (s->cur_X - s->prev_X) * (o->earliest_unpriced_expi - s->prev_time) / o->init_step_size;
     o->final_value = (o->accumulated_value + step_interpolation) / o->earliest_unpriced_expi;
+    double log_interpolation = (s->log_X - s->prev_log_X) *
+                               (o->earliest_unpriced_expi - s->prev_time) / o->init_step_size;
+    /* the interpolation term has weights +x and -x: it does not change their sum */
+    o->final_log = (o->accumulated_log + log_interpolation) / o->accumulated_weight;
   } else {
     o->final_value = s->prev_X + (s->cur_X - s->prev_X) *
                                      (o->earliest_unpriced_expi - s->prev_time) /
@@ -387,6 +403,7 @@ static void qe_step_drift(const oracle_hparams *p, sde_state *st, const policy *
   double K_4 = gamma_2 * delta * (1 - rho * rho);                             /* :79 */
   if (drift_mode == 1) /* NOT the reference: Andersen's K0* in place of K0 */
     K_0 = oracle_qe_k0_star(p, delta, st->prev_V, NULL, NULL);
+  st->prev_log_X = st->log_X;
   st->log_X = st->log_X + K_0 + K_1 * st->prev_V + K_2 * st->cur_V +
               sqrt(K_3 * st->prev_V + K_4 * st->cur_V) * d->spot_normal(d);   /* :80 */
   st->prev_X = st->cur_X;                                                     /* :81 */
@@ -445,7 +462,7 @@ static uint32_t simulate_path(const oracle_contract *c, draw_src *d, int trailin
   update_earliest(&o, c->expiries[0], (double)c->steps);            /* :33 */
   policy_reset(&o);                                                 /* :34 */
   /* heston_sde = initial_state: HSimulation.tpp:26, :87-94 */
-  sde_state st = {c->S, c->p.v_0, c->S, c->p.v_0, 0.0, 0.0, log(c->S)};
+  sde_state st = {c->S, c->p.v_0, c->S, c->p.v_0, 0.0, 0.0, log(c->S), log(c->S)};
   if (n_opts == 0) return 0;
   qe_step_drift(&c->p, &st, &o, d, c->drift_mode);                  /* :35 ++(sde=init) */
   n_steps = 1;
@@ -478,10 +495,26 @@ typedef struct {
   double n_sims;
   /* control variate c = final value - S (include/hexo_gpu.h, HEXO_CV_UNDERLYING); may be NULL */
   double *cross, *ctl, *ctl2;
+  /* geometric != 0 (HEXO_CV_GEOMETRIC): the control is per option, c_j = max(G - K_j, 0) with
+   * G = exp(final_log); cross / ctl / ctl2 then hold n_opts entries each */
+  int geometric;
 } sum_sink;
 
 static void pay_sums(void *ctx, uint32_t chain, const policy *o) {
   sum_sink *k = (sum_sink *)ctx;
+  if (k->geometric) {
+    const double G = exp(o->final_log);
+    for (uint32_t j = k->c->strike_offsets[chain]; j < k->c->strike_offsets[chain + 1]; ++j) {
+      const double pf = final_payoff(o, k->c->strikes[j]);
+      const double cg = G - k->c->strikes[j] > 0.0 ? G - k->c->strikes[j] : 0.0;
+      k->sum[j] += pf;
+      k->sumsq[j] += pf * pf;
+      k->cross[j] += pf * cg;
+      k->ctl[j] += cg;
+      k->ctl2[j] += cg * cg;
+    }
+    return;
+  }
   for (uint32_t j = k->c->strike_offsets[chain]; j < k->c->strike_offsets[chain + 1]; ++j) {
     double pf = final_payoff(o, k->c->strikes[j]);
     if (k->prices) k->prices[j] += pf / k->n_sims;                  /* :40 */
@@ -522,7 +555,7 @@ int oracle_price_ref(const oracle_contract *c, unsigned int n_sims, unsigned int
   if (prices) memset(prices, 0, n_opts * sizeof(double));           /* :22 */
   if (sum) memset(sum, 0, n_opts * sizeof(double));
   if (sumsq) memset(sumsq, 0, n_opts * sizeof(double));
-  sum_sink sink = {c, prices, sum, sumsq, (double)n_sims, NULL, NULL, NULL};
+  sum_sink sink = {c, prices, sum, sumsq, (double)n_sims, NULL, NULL, NULL, 0};
   for (unsigned int tid = 0; tid < nthreads; ++tid) {               /* :23 */
     const unsigned int local_sims = n_sims / nthreads;              /* :27 */
     oracle_rng *rng = oracle_rng_new(rand_buf_size, 1u << tid, normal_mode); /* :28 */
@@ -551,7 +584,7 @@ int oracle_price_stream_rng(const oracle_contract *c, int rng_mode, uint64_t see
   const uint32_t n_opts = c->strike_offsets[c->n_chains];
   if (sum) memset(sum, 0, n_opts * sizeof(double));
   if (sumsq) memset(sumsq, 0, n_opts * sizeof(double));
-  sum_sink sink = {c, NULL, sum, sumsq, (double)n_paths, NULL, NULL, NULL};
+  sum_sink sink = {c, NULL, sum, sumsq, (double)n_paths, NULL, NULL, NULL, 0};
   const uint64_t base = n_paths / n_streams_total, rem = n_paths % n_streams_total;
   for (uint64_t s = stream_begin; s < stream_begin + stream_count; ++s) {
     stream_ctx sc;
@@ -580,8 +613,8 @@ static uint32_t simulate_path_exact(const oracle_contract *c, draw_src *d, pay_f
   policy o;
   memset(&o, 0, sizeof(o));
   o.payoff = c->payoff;
-  sde_state st = {c->S, c->p.v_0, c->S, c->p.v_0, 0.0, 0.0, log(c->S)};
-  double integral = 0.0, t_prev = 0.0;
+  sde_state st = {c->S, c->p.v_0, c->S, c->p.v_0, 0.0, 0.0, log(c->S), log(c->S)};
+  double integral = 0.0, integral_log = 0.0, t_prev = 0.0;
   uint32_t total = 0;
   for (uint32_t k = 0; k < c->n_chains; ++k) {
     const double span = c->expiries[k] - t_prev;
@@ -592,9 +625,11 @@ static uint32_t simulate_path_exact(const oracle_contract *c, draw_src *d, pay_f
     for (long long j = 0; j < n; ++j) {
       qe_step_drift(&c->p, &st, &o, d, c->drift_mode);
       integral += o.init_step_size * .5 * (st.cur_X + st.prev_X);
+      integral_log += o.init_step_size * .5 * (st.log_X + st.prev_log_X);
       ++total;
     }
     o.final_value = c->payoff == ORACLE_ASIAN ? integral / c->expiries[k] : st.cur_X;
+    o.final_log = integral_log / c->expiries[k]; /* full trapezoid rule: the weights sum to T_k */
     pay(pay_ctx, k, &o);
     t_prev = c->expiries[k];
   }
@@ -610,7 +645,7 @@ int oracle_price_stream_exact(const oracle_contract *c, int rng_mode, uint64_t s
   const uint32_t n_opts = c->strike_offsets[c->n_chains];
   if (sum) memset(sum, 0, n_opts * sizeof(double));
   if (sumsq) memset(sumsq, 0, n_opts * sizeof(double));
-  sum_sink sink = {c, NULL, sum, sumsq, (double)n_paths, NULL, NULL, NULL};
+  sum_sink sink = {c, NULL, sum, sumsq, (double)n_paths, NULL, NULL, NULL, 0};
   const uint64_t base = n_paths / n_streams_total, rem = n_paths % n_streams_total;
   for (uint64_t s = stream_begin; s < stream_begin + stream_count; ++s) {
     stream_ctx sc;
@@ -641,7 +676,45 @@ int oracle_price_stream_cv(const oracle_contract *c, int rng_mode, int exact_gri
   const uint32_t n_opts = c->strike_offsets[c->n_chains];
   memset(out, 0, (3 * (size_t)n_opts + 2 * (size_t)c->n_chains) * sizeof(double));
   sum_sink sink = {c, NULL, out, out + n_opts, (double)n_paths, out + 2 * (size_t)n_opts,
-                   out + 3 * (size_t)n_opts, out + 3 * (size_t)n_opts + c->n_chains};
+                   out + 3 * (size_t)n_opts, out + 3 * (size_t)n_opts + c->n_chains, 0};
+  const uint64_t base = n_paths / n_streams_total, rem = n_paths % n_streams_total;
+  for (uint64_t s = stream_begin; s < stream_begin + stream_count; ++s) {
+    stream_ctx sc;
+    memset(&sc, 0, sizeof(sc));
+    uint64_t sd[4] = {seed, s, 0, 0};
+    prng_init(&sc.s, sd);
+    sc.pos = 16;
+    sc.normal_mode = normal_mode;
+    sc.rng_mode = rng_mode;
+    sc.seed = seed;
+    sc.stream = s;
+    draw_src d = {strsrc_gv, strsrc_uv, strsrc_gx, strsrc_end, &sc};
+    const uint64_t my_paths = base + (s < rem ? 1 : 0);
+    for (uint64_t i = 0; i < my_paths; ++i) {
+      if (exact_grid)
+        simulate_path_exact(c, &d, pay_sums, &sink);
+      else
+        simulate_path(c, &d, 0, pay_sums, &sink);
+    }
+  }
+  return 0;
+}
+
+/* Stream pricer with the sums of the geometric-Asian control variate (include/hexo_gpu.h,
+ * HEXO_CV_GEOMETRIC; NOT in the reference): out = [sum pf | sum pf^2 | sum pf c | sum c |
+ * sum c^2], n_opts entries each, c_j = max(G - K_j, 0), G = exp of the policy's accumulation
+ * applied to ln X.  Asian contracts only. */
+int oracle_price_stream_geo(const oracle_contract *c, int rng_mode, int exact_grid, uint64_t seed,
+                            uint64_t n_paths, uint64_t n_streams_total, uint64_t stream_begin,
+                            uint64_t stream_count, int normal_mode, double *out) {
+  int rc = check_contract(c);
+  if (rc) return rc;
+  if (c->payoff != ORACLE_ASIAN) return -1;
+  if (n_streams_total == 0 || stream_begin + stream_count > n_streams_total || !out) return -1;
+  const size_t n_opts = c->strike_offsets[c->n_chains];
+  memset(out, 0, 5 * n_opts * sizeof(double));
+  sum_sink sink = {c, NULL, out, out + n_opts, (double)n_paths, out + 2 * n_opts,
+                   out + 3 * n_opts, out + 4 * n_opts, 1};
   const uint64_t base = n_paths / n_streams_total, rem = n_paths % n_streams_total;
   for (uint64_t s = stream_begin; s < stream_begin + stream_count; ++s) {
     stream_ctx sc;

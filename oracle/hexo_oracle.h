@@ -121,6 +121,13 @@ int oracle_price_stream_cv(const oracle_contract *c, int rng_mode, int exact_gri
                            uint64_t n_paths, uint64_t n_streams_total, uint64_t stream_begin,
                            uint64_t stream_count, int normal_mode, double *out);
 
+/* The same with the geometric-Asian control variate (NOT in the reference either): Asian
+ * contracts only; out = [sum pf | sum pf^2 | sum pf c | sum c | sum c^2], n_opts entries each,
+ * c_j = max(G - K_j, 0), G = exp(the Asian policy's accumulation applied to ln X). */
+int oracle_price_stream_geo(const oracle_contract *c, int rng_mode, int exact_grid, uint64_t seed,
+                            uint64_t n_paths, uint64_t n_streams_total, uint64_t stream_begin,
+                            uint64_t stream_count, int normal_mode, double *out);
+
 /* ---- tape replay ------------------------------------------------------------
  * tape[path][step][3] = {Z_V, U_V, Z_X}; the stepper takes Z_V or U_V according
  * to its branch.  finals[path][chain] receives the policy's final_value (Asian

@@ -79,6 +79,7 @@ def oracle() -> C.CDLL:
         o.oracle_price_stream_cv.argtypes = [C.POINTER(OracleContract), C.c_int, C.c_int,
                                              C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64,
                                              C.c_uint64, C.c_int, dp]
+        o.oracle_price_stream_geo.argtypes = o.oracle_price_stream_cv.argtypes
         o.oracle_philox4x32_10.argtypes = [C.POINTER(C.c_uint32)] * 3
         o.oracle_philox4x32_10.restype = None
         o.oracle_replay.argtypes = [C.POINTER(OracleContract), dp, C.c_uint64, C.c_uint32, dp]
@@ -170,6 +171,18 @@ class Contract:
         rc = oracle().oracle_price_stream_cv(C.byref(self.c), rng_mode, int(exact_grid), seed,
                                              n_paths, n_streams, begin, count, normal_mode,
                                              out.ctypes.data_as(dp))
+        assert rc == 0, rc
+        return out
+
+    def price_stream_geo(self, seed, n_paths, n_streams, begin=0, count=None,
+                         normal_mode=NORMAL_F32, rng_mode=0, exact_grid=False):
+        """All sums of a geometric-control request: [pf | pf^2 | pf c | c | c^2] per option,
+        c = max(G - K, 0) with G the geometric average on the arithmetic average's weights."""
+        count = n_streams - begin if count is None else count
+        out = np.zeros(5 * self.n_opts)
+        rc = oracle().oracle_price_stream_geo(C.byref(self.c), rng_mode, int(exact_grid), seed,
+                                              n_paths, n_streams, begin, count, normal_mode,
+                                              out.ctypes.data_as(dp))
         assert rc == 0, rc
         return out
 
