@@ -101,20 +101,6 @@ __device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
   return d;
 }
 
-// far tail of as241.f90:110-114 (r > 5, i.e. p < 1.4e-11) and the p in {0,1} case
-// (:99-103): rare, evaluated in plain scalar code
-static __device__ __noinline__ float ppnd_far_tail_f32(float q, float t) {
-  using P = Ppnd;
-  if (!(t < 3.0e38f)) return 0.0f;  // v == 0: the reference returns 0 with IFAULT = 1
-  const float r = sqrtf(t) - (float)P::SPLIT2;
-  const float z =
-      horner8<float>(r, (float)P::E7, (float)P::E6, (float)P::E5, (float)P::E4, (float)P::E3,
-                     (float)P::E2, (float)P::E1, (float)P::E0) /
-      horner8<float>(r, (float)P::F7, (float)P::F6, (float)P::F5, (float)P::F4, (float)P::F3,
-                     (float)P::F2, (float)P::F1, 1.0f);
-  return q < 0.0f ? -z : z;
-}
-
 // Phase 1 (F32 mode): the central formula for two draws at once (as241.f90:88-92).
 // tail0/tail1 are set when |q| > 0.425; such draws get their value from
 // normal_tail_f32 afterwards (z0/z1 then hold a finite placeholder).
@@ -145,36 +131,13 @@ __device__ __forceinline__ void normal2_central_f32(uint64_t w0, uint64_t w1, fl
   unpack2(fmul2(num, pack2(mufu_rcp(d0), mufu_rcp(d1))), z0, z1);
 }
 
-// Phase 2 (F32 mode): a draw outside the central region (as241.f90:94-116).  The tail
-// argument min(p, 1-p) uses all 64 bits of the draw.  Branch-free intermediate-tail
-// formula (:104-109); *t = -ln(min(p, 1-p)) tells the caller whether the far tail
-// (t > 25, i.e. r > 5, p < 1.4e-11, or p in {0,1}) has to replace the value.
-__device__ __forceinline__ float normal_tail_mid_f32(uint64_t w, float& t) {
-  using P = Ppnd;
-  const uint32_t hi = (uint32_t)(w >> 32), lo = (uint32_t)w;
-  const uint32_t flip = (uint32_t)((int32_t)hi >> 31);  // all ones when p >= 1/2
-  // v = p (p < 1/2) or ~p ~ 1 - p as a 64-bit fraction; vf = v 2^-32
-  const float vf = fmaf((float)(lo ^ flip), 2.3283064365386963e-10f, (float)(hi ^ flip));
-  // t = -ln(v 2^-64) = (32 - lg2(vf)) ln2 >= 0,  r = sqrt(t)
-  t = fmaf(mufu_lg2(vf), -0.69314718055994530942f, 22.180709777918249f);
-  const float r = mufu_sqrt(t) - (float)P::CONST2;
-  const float z =
-      horner8<float>(r, (float)P::C7, (float)P::C6, (float)P::C5, (float)P::C4, (float)P::C3,
-                     (float)P::C2, (float)P::C1, (float)P::C0) *
-      mufu_rcp(horner8<float>(r, (float)P::D7, (float)P::D6, (float)P::D5, (float)P::D4,
-                              (float)P::D3, (float)P::D2, (float)P::D1, 1.0f));
-  // sign of q = p - 1/2: negative when the top bit of the draw is clear (as241.f90:116)
-  // as ONE lop3 (z ^ (~hi & 0x80000000), truth table 0xD2); left to the compiler this becomes a
-  // lop3 plus a negating add
-  uint32_t zs;
-  asm("lop3.b32 %0, %1, %2, 0x80000000, 0xD2;" : "=r"(zs) : "r"(__float_as_uint(z)), "r"(hi));
-  return __uint_as_float(zs);
-}
-
-// Two tail draws per call, the arithmetic of normal_tail_mid_f32 with every step that has a
-// packed form done for both at once: v 2^-32, t, r - 1.6, the C / D Horner chains (14 FFMA2
-// instead of 28 FFMA) and the final product.  fma.rn.f32x2 is two IEEE fmas, so each half is
-// bit-identical to the scalar routine.
+// Phase 2 (F32 mode): draws outside the central region (as241.f90:94-116), two per call.  The
+// tail argument min(p, 1-p) uses all 64 bits of the draw: v = p (p < 1/2) or ~p ~ 1 - p as a 64-bit
+// fraction, t = -ln(v 2^-64) = (32 - lg2(v 2^-32)) ln2 >= 0, r = sqrt(t), then the intermediate-
+// tail formula (:104-109), branch-free; t tells the caller whether the far tail (t > 25, i.e.
+// r > 5, p < 1.4e-11, or p in {0,1}) has to replace the value.  Every step that has a packed form
+// is done for both draws at once: v 2^-32, t, r - 1.6, the C / D Horner chains (14 FFMA2 instead
+// of 28 FFMA) and the final product; fma.rn.f32x2 is two IEEE fmas.
 template <bool P7 = false>
 __device__ __forceinline__ void normal2_tail_mid_f32(uint64_t w0, uint64_t w1, float& z0, float& z1,
                                                      float& t0, float& t1) {
@@ -207,10 +170,14 @@ __device__ __forceinline__ void normal2_tail_mid_f32(uint64_t w0, uint64_t w1, f
   z1 = __uint_as_float(s1);
 }
 
-// the far tail for the same draw (rare)
+// The far tail for the same draw (rare: t > 25, i.e. min(p, 1-p) < 1.4e-11, or p in {0, 1}).
+// Out here the reference's own arithmetic matters: it forms p = RN(w) 2^-64 in double first
+// (RNG.cpp:31), so the top 1024 words ARE p = 1 (-> 0 with IFAULT, as241.f90:99-103) and 1 - p is
+// a multiple of 2^-53, while the bit pattern ~w used above is exact.  The scalar as-built routine
+// on the reference's p reproduces all of that.
 static __device__ __noinline__ float normal_tail_far_f32(uint64_t w, float t) {
-  const uint32_t hi = (uint32_t)(w >> 32);
-  return ppnd_far_tail_f32((hi & 0x80000000u) ? 1.0f : -1.0f, t);
+  (void)t;
+  return (float)ppnd16_f32(u64_to_unit(w));
 }
 
 // ---- double precision ---------------------------------------------------------

@@ -253,7 +253,7 @@ def test_gpu_unknown_control_variate_is_refused(gpu):
     rq = pricing._Request(hx.HQEAnderson(hx.AAsianCallNonAdaptive), hx.HParams(*oa.DEFAULT_PARAMS),
                           100.0, [hx.OptionsChain.from_strikes(1.0, [100.0])], 100, 1, 10, 1,
                           "f32", 32)
-    rq.req.control_variate = 2
+    rq.req.control_variate = 7
     sums = np.zeros(8)
     assert gpu.hexo_gpu_price_shard(C.byref(rq.req), 0, 32, sums.ctypes.data_as(_lib.c_double_p),
                                     None) == -1

@@ -275,3 +275,17 @@ def test_normals_from_words_is_the_scalar_composition():
         z = oa.normals_from_words(words, mode)
         assert np.array_equal(z, oa.ppnd16(oa.u64_to_unit(words), mode))
         assert z[-3] == 0.0 and z[-2] == 0.0 and z[-1] == 0.0
+
+
+def test_shishua_stream_digest_is_pinned():
+    """SHA-256 of the first MiB for the seeds of the reference's first three threads equals the
+    committed digest (tests/golden/shishua_sha256.json, written by make_shishua_digest.py, which
+    can also diff it against upstream shishua where a network exists)."""
+    import hashlib
+    import json
+    with open(os.path.join(ROOT, "tests", "golden", "shishua_sha256.json")) as f:
+        gold = json.load(f)
+    for key, want in gold["sha256"].items():
+        seed = tuple(int(x) for x in key.split(","))
+        got = hashlib.sha256(oa.shishua_bytes(seed, gold["bytes"]).tobytes()).hexdigest()
+        assert got == want, key

@@ -36,3 +36,31 @@ run("cfg4 asian 1024", A, [1.0], [[100.0]], int(2e7*scale), 1024, "f64")
 run("cfg4 asian 1024", A, [1.0], [[100.0]], int(2e7*scale), 1024, "f32", rng="philox")
 run("cfg4 asian martingale", A, [1.0], [[100.0]], int(2e7*scale), 1024, "f32", drift="martingale")
 run("cfg1 asian 100k", A, [1.0], [[100.0]], 100_000, 252, "f32", reps=4)
+
+# cfg1 (the reference's own CLI size): how the stream count fills the machine
+for ns in (0, 65536, 50000, 37888):
+    ch = [hx.OptionsChain.from_strikes(1.0, [100.0])]
+    best = None
+    for i in range(4):
+        r = hx.price_full(A, p, 100.0, ch, 100_000, 1, 252, seed=1, n_streams=ns)
+        if i and (best is None or r.kernel_ms < best.kernel_ms): best = r
+    print(f"cfg1 100k paths n_streams={best.n_streams:6d} grid={best.grid} ms={best.kernel_ms:.3f} "
+          f"rate={best.path_steps/best.kernel_ms/1e6:7.2f} G/s", flush=True)
+# cfg3 as SURVEY 8(d) defines it: 8 independent single-maturity pricings (64 strikes, 1e7 paths x 252
+# steps each), submitted as one batch through the C ABI
+import ctypes as C
+from hestonexotics_b200 import pricing
+K64 = list(np.linspace(70, 130, 64))
+n3 = int(1e7 * min(scale, 1.0))
+rqs = [pricing._Request(A, p, 100.0, [hx.OptionsChain.from_strikes(0.25 * k, K64)], n3, 64, 252, 1, "f32", 0)
+       for k in range(1, 9)]
+arr = (_lib.HexoPriceRequest * 8)(*[r.req for r in rqs])
+prices, se = np.zeros(8 * 64), np.zeros(8 * 64)
+stats = (_lib.HexoGpuStats * 8)()
+for lanes in (1, 8):
+    for rep in range(2):
+        _lib.check(lib.hexo_gpu_price_batch(arr, 8, lanes, prices.ctypes.data_as(_lib.c_double_p),
+                                            se.ctypes.data_as(_lib.c_double_p), stats))
+    ms = stats[0].kernel_ms
+    print(f"cfg3 as 8 independent pricings (batch, {lanes} lane(s)): n={n3:.0e} x 252 x 8 ms={ms:8.2f} "
+          f"rate={8 * n3 * 252 / ms / 1e6:7.2f} G/s  ATM prices {prices.reshape(8, 64)[:, 32].round(4)}", flush=True)
