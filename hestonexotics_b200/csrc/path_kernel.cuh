@@ -648,8 +648,10 @@ heston_qe_paths_kernel(const __grid_constant__ PathArgs a) {
                 const bool rare_x = grow_spot_is_rare(delta);
                 if (rare_x | mid.rare) {
                   if (rare_x) Xn = grow_spot_rare(X, delta, exptab_s);
-                  if (qe_rare_again(mid))
-                    Vn = qe_variance_rare<MART>(g, V, mid, [&]() { return uniform_at(za); });
+                  if (mid.rare) {
+                    if (qe_rare_exact(mid))
+                      Vn = qe_variance_rare<MART>(g, V, mid, [&]() { return uniform_at(za); });
+                  }
                 }
                 X = Xn;
                 sumX += X;
@@ -663,8 +665,10 @@ heston_qe_paths_kernel(const __grid_constant__ PathArgs a) {
                   Xprev = X;
                   X = fast_exp(lnX, exptab_s);
                 }
-                if (mid.rare)
-                  Vn = qe_variance_rare<MART>(g, V, mid, [&]() { return uniform_at(za); });
+                if (mid.rare) {
+                  if (qe_rare_exact(mid))
+                    Vn = qe_variance_rare<MART>(g, V, mid, [&]() { return uniform_at(za); });
+                }
               }
               Vold = V;
               V = Vn;
@@ -720,6 +724,7 @@ heston_qe_paths_kernel(const __grid_constant__ PathArgs a) {
                                   my_sum + g.first_opt, my_sq + g.first_opt,
                                   my_cross + g.first_opt, my_ctl + g.first_opt,
                                   my_ctl + a.n_opts + g.first_opt);
+        __syncwarp();  // gbuf is the tail list's storage: the next refill writes it again
       } else {
         accumulate_with_control(fvbuf, amask, lane, a.strikes + g.first_opt, g.n_strikes, a.S,
                                 my_sum + g.first_opt, my_sq + g.first_opt, my_cross + g.first_opt,

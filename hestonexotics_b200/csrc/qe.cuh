@@ -60,8 +60,8 @@ struct SegConst {
 // stops ptxas from interleaving the two dependency chains).
 struct QeVarMid {
   double m, s2h;  // :59, :60 (s^2/2)
-  bool rare;      // psi >= 1.5: the quadratic value has to be replaced by qe_variance_rare
-  int t_hi;       // high word of 3 w - s^2/2, what `rare` was read from (rare_again())
+  bool rare;      // psi >= 1.5 is POSSIBLE (decided on high words): qe_rare_exact() settles it, and
+                  // then the quadratic value has to be replaced by qe_variance_rare
   double k0;      // MART only: K0* + (K1 + K3/2) V = -ln M of this step
 };
 
@@ -82,11 +82,13 @@ __device__ __forceinline__ double qe_variance_quad(const SegConst& g, const doub
   const double me = fast_sqrt_signed(fma(sw, dm, kFm.tiny));
   mid.m = m;
   mid.s2h = s2h;
-  // :63  psi >= 1.5  <=>  3 w <= s^2/2.  Read off the sign of 3 w - s^2/2 on the integer pipe
-  // (the high word; a positive denormal counts as zero, where both branches are valid) instead of
-  // a multiply and a compare on the FP64 pipe.
-  mid.t_hi = __double2hiint(fma(3.0, w, -s2h));
-  mid.rare = mid.t_hi <= 0;
+  // :63  psi < 1.5  <=>  3 w > s^2/2  <=>  sqrt(w) > m/2  <=>  sw > dm.  The hot path only compares
+  // the HIGH WORDS of sw and dm on the integer pipe (both are positive doubles, so their bit
+  // patterns order like their values; a NaN sw -- psi > 2 -- makes dm the same NaN): "sw's high
+  // word is larger" proves psi < 1.5; anything else, including equal high words (sw and dm within
+  // 2^-20 of each other, one step in a million), goes to the rare block, where qe_rare_exact
+  // takes the decision with the exact comparison.  No FP64 instruction for the test per step.
+  mid.rare = __double2hiint(sw) <= __double2hiint(dm);
   if (MART) {
     const double d = fma(-g.A2, dm, 1.0);                   // 1 - 2 A a
     const double k0 = fma(0.5, fast_log(d), -(g.A * sw) * fast_rcp(d));
@@ -96,13 +98,12 @@ __device__ __forceinline__ double qe_variance_quad(const SegConst& g, const doub
   return fma(zv, fma(dm, zv, me + me), sw);                 // :64-68
 }
 
-// `mid.rare` once more, for code that already sits behind a branch on it together with other
-// conditions: recomputed from the integer there, so that the hot path does not keep a second
-// predicate alive for it (ptxas otherwise issues the compare twice per step)
-__device__ __forceinline__ bool qe_rare_again(const QeVarMid& mid) {
-  int t = mid.t_hi;
-  asm volatile("" : "+r"(t));
-  return t <= 0;
+// The exact decision psi >= 1.5  <=>  3 w - s^2/2 <= 0 (read off the sign of the high word; a
+// positive denormal counts as zero, where both branches are valid), for code that already sits
+// behind the cheap test mid.rare.
+__device__ __forceinline__ bool qe_rare_exact(const QeVarMid& mid) {
+  const double w = fma(mid.m, mid.m, -mid.s2h);
+  return __double2hiint(fma(3.0, w, -mid.s2h)) <= 0;
 }
 
 // Exponential / zero-mass branch (:70-73), a few per cent of the warp-steps, straight-line
@@ -145,7 +146,9 @@ __device__ __forceinline__ double qe_variance(const SegConst& g, const double V,
                                               const UniformFn& uv, double* k0 = nullptr) {
   QeVarMid mid;
   double Vn = qe_variance_quad<MART>(g, V, zv, mid);
-  if (mid.rare) Vn = qe_variance_rare<MART>(g, V, mid, uv);
+  if (mid.rare) {
+    if (qe_rare_exact(mid)) Vn = qe_variance_rare<MART>(g, V, mid, uv);
+  }
   if (MART) *k0 = mid.k0;
   return Vn;
 }
