@@ -43,10 +43,12 @@ struct payoff_of<HQEAnderson<ffloat, EuropeanCallNonAdaptive>> {
 
 struct GpuPriceOptions {
   uint64_t seed = 1;                      // the reference's thread-0 seed (HSimulation.tpp:28)
-  int normal_mode = HEXO_NORMAL_F32;      // the reference as built (as241.f90:20-25)
+  int normal_mode = HEXO_NORMAL_F32;      // the reference as built (as241.f90:20-25); optional:
+                                          // HEXO_NORMAL_F64, HEXO_NORMAL_F32_PPND7
   int rng_mode = HEXO_RNG_SHISHUA;        // the reference's generator; HEXO_RNG_PHILOX optional
   int schedule_mode = HEXO_SCHEDULE_REFERENCE;  // the reference's time grid, quirks included
-  int control_variate = HEXO_CV_NONE;     // HEXO_CV_UNDERLYING: prices and errors use c = A_T - S
+  int control_variate = HEXO_CV_NONE;     // HEXO_CV_GEOMETRIC (Asian): the control HSimulation.h:51
+                                          // suggests; HEXO_CV_UNDERLYING: c = final value - S
   int drift_mode = HEXO_DRIFT_REFERENCE;  // HEXO_DRIFT_MARTINGALE: Andersen's K0* per step
   uint64_t n_streams = 0;                 // 0 = sized for the device(s)
   int n_gpus = 1;                         // devices of this process to spread over; 0 = all
