@@ -119,15 +119,17 @@ __device__ __forceinline__ double qe_variance_rare(const SegConst& g, const doub
   const double m = mid.m;
   const double m2 = m * m, s2 = mid.s2h + mid.s2h;
   const double q = m2 + s2;
-  // U = 1.0 (probability 2^-54) would make the reference take log(x/0) = inf;
-  // clamp to the largest double below 1 instead.
-  const double u = fmin(uv(), kFm.u_max);                   // :72
+  // U = 1.0 (probability 2^-54) would make the reference take log(x/0) = inf; clamp it below 1
+  // instead -- on the high word (U is in [0, 1]: only U = 1 has the high word 0x3ff00000, and its
+  // low word is 0), one integer min where fmin costs five instructions for its NaN rules.
+  const double u0 = uv();                                   // :72
+  const double u = __hiloint2double(min(__double2hiint(u0), 0x3fefffff), __double2loint(u0));
   double v = 0.0;
   // p >= 0.2 here, and a warp rarely has more than one lane on this path: testing U against p
   // first skips the logarithm (the longest dependency chain of the kernel) about as often
   if (s2 - m2 < u * q) {                                    // :73  p < U
-    const double y = (m2 + m2) * fast_rcp(q * (1.0 - u));
-    v = 0.5 * q * fast_rcp(m) * fast_log(y);
+    const double y = (m2 + m2) * fast_rcp(q * (1.0 - u));   // = (1-p)/(1-U) > 1 because p < U
+    v = 0.5 * q * fast_rcp(m) * fast_log_ge1(y);
   }
   if (MART) {
     const double d = fma(-g.A, q, m + m);                   // (beta - A) q
