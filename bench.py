@@ -388,7 +388,7 @@ def run_ours(args):
                 "value": rate, "unit": "path-steps/s", "cores": used, "kind": kind,
                 "sample": f"{sample} paths x {STEPS} steps of the cfg4 contract, {secs:.1f} s, "
                           f"price {cprice:.4f}"}
-            if not args.no_extras and args.workload == "cfg4":
+            if not args.no_extras and args.workload == "cfg4" and world == 1:
                 out["price_z_vs_reference"] = reference_z_score(price, se, n_paths, steps)
         print(json.dumps(out))
     if world > 1:

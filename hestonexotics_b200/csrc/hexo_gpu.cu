@@ -524,7 +524,7 @@ static int finish_prices(const hexo_price_request* r, const double* sums, double
       // sums = [pf | pf^2 | pf c | c | c^2], n_opts each
       std::vector<double> eg;
       const int rg = geometric_asian_means(r, segs, eg);
-      if (rg) return rg;
+      if (rg) return fail(rg, "the geometric-Asian control's mean is not finite for these parameters");
       const double n = (double)r->n_paths;
       const double *sp = sums, *sq = sums + n_opts, *sx = sums + 2 * (size_t)n_opts,
                    *sc = sums + 3 * (size_t)n_opts, *sc2 = sums + 4 * (size_t)n_opts;
@@ -936,7 +936,7 @@ int hexo_heston_geometric_asian(const hexo_price_request* req, double* means_out
   if (rc) return rc;
   std::vector<double> eg;
   rc = geometric_asian_means(req, segs, eg);
-  if (rc) return rc;
+  if (rc) return fail(rc, "the geometric-Asian control's mean is not finite for these parameters");
   for (size_t j = 0; j < eg.size(); ++j) means_out[j] = eg[j];
   return HEXO_OK;
 }

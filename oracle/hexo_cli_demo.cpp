@@ -9,7 +9,9 @@
  * loop is the reference's own format (src/Main.cpp:89-93), using the reference's imp_vol
  * (src/BSM.cpp, compiled verbatim).
  *
- *   hexo_cli_demo <chain.csv> [v_0 v_m rho kappa sigma] [n_simulations steps]
+ *   hexo_cli_demo <chain.csv> [v_0 v_m rho kappa sigma] [n_simulations steps] [geometric]
+ * a trailing `geometric` prices with the geometric-Asian control variate (the one the reference
+ * suggests at src/inc/HSimulation.h:51) through GpuPriceOptions -- same output format.
  * chain.csv:  first line `S,<spot>`; then `days_to_expiry,strike,bid,ask,volume` per option,
  * grouped by expiry in increasing order.
  */
@@ -72,7 +74,8 @@ static underlying_data load_chain_file(const char* path) {
 
 int main(int argc, char** argv) {
   if (argc < 2) {
-    std::cerr << "usage: hexo_cli_demo <chain.csv> [v_0 v_m rho kappa sigma] [n_simulations steps]\n";
+    std::cerr << "usage: hexo_cli_demo <chain.csv> [v_0 v_m rho kappa sigma] [n_simulations steps] "
+                 "[geometric]\n";
     return 2;
   }
   try {
@@ -83,9 +86,11 @@ int main(int argc, char** argv) {
     const unsigned steps = argc >= 9 ? atoi(argv[8]) : 1000;    // 1e+3
     std::cout << "params, v0: " << p.v_0 << "\tv_m: " << p.v_m << "\trho: " << p.rho
               << "\tkappa: " << p.kappa << "\tsigma: " << p.sigma << std::endl;  // Main.cpp:87
+    HSimulation::GpuPriceOptions opt;
+    if (argc >= 10 && std::string(argv[9]) == "geometric") opt.control_variate = HEXO_CV_GEOMETRIC;
     std::vector<ffloat> results =
         HSimulation::price_gpu<HSimulation::HQEAnderson<ffloat, AAsianCallNonAdaptive>>(
-            p, ddata.S, ddata.all_chains, n_sim, length(ddata.all_chains), steps);
+            p, ddata.S, ddata.all_chains, n_sim, length(ddata.all_chains), steps, opt);
     unsigned int i = 0;
     for (const options_chain& opt_chain : ddata.all_chains)
       for (const option& opt : opt_chain.options)  // Main.cpp:90-93

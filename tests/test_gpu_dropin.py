@@ -58,3 +58,23 @@ def test_cli_demo_prints_reference_format(gpu):
     pr = np.array(prices).reshape(3, 3)
     assert (np.diff(pr, axis=1) < 0).all()          # falls with the strike within each expiry
     assert 1.0 < pr[0, 1] < 2.0 and pr[2, 1] > pr[1, 1] > pr[0, 1]   # ATM Asian grows with expiry
+
+
+def test_cli_demo_with_the_geometric_control(gpu):
+    """The same CLI with `geometric` appended: GpuPriceOptions::control_variate through the C++
+    adapter.  10^5 paths with the control agree with 4*10^6 plain paths within a few cents."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "hexo_cli_demo")
+    chain = os.path.join(ROOT, "tests", "golden", "synthetic_chain.csv")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/hexo_cli_demo not built (needs the reference tree at build time)")
+
+    def run(*extra):
+        out = subprocess.run([exe, chain, "0.04", "0.04", "-0.7", "2.0", "0.5", *extra],
+                             capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stdout + out.stderr
+        return np.array([float(dict(f.split(": ") for f in ln.split("\t"))["asian-option-price"])
+                         for ln in out.stdout.strip().splitlines()[1:]])
+    plain = run("4000000", "252")
+    cv = run("100000", "252", "geometric")
+    assert plain.shape == cv.shape == (9,)
+    assert np.abs(cv - plain).max() < 0.02, (cv, plain)
