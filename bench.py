@@ -44,7 +44,7 @@ FLOP_PER_PATH_STEP = 100.0  # SURVEY.md section 8(d), Asian
 # Measured constants of the path kernel (profiles/, ncu captures of the same kernel build; they do
 # not depend on the job size): FP64 instructions issued per path-step, of which FMA, and the
 # kernel's DRAM traffic per launch.  bench.py reports them next to the algorithmic figure.
-FP64_ISSUED_PER_PATH_STEP = {"instr": 42.75, "flop": 42.75 + 29.03}   # DFMA counts two flop
+FP64_ISSUED_PER_PATH_STEP = {"instr": 41.19, "flop": 41.19 + 28.39}   # DFMA counts two flop
 NCU_PROFILE = "profiles/r02_path_kernel_ncu_keys.txt"
 WORKLOADS = {
     # name: (params, expiry, strikes, steps, paths, description)
@@ -355,8 +355,8 @@ def run_ours(args):
             "roofline": {
                 "bound": "fp64", "achieved": achieved / 1e12, "peak": fl.value / 1e12,
                 "unit": "TFLOP/s", "frac": achieved / fl.value,
-                # what the FP64 pipe really executes: the kernel issues 42.75 FP64 instructions per
-                # path-step (29.0 of them FMAs), not the 100 flop of the reference algorithm --
+                # what the FP64 pipe really executes: the kernel issues 41.19 FP64 instructions per
+                # path-step (28.4 of them FMAs), not the 100 flop of the reference algorithm --
                 # 66 of those belong to PPND16, which this normal mode evaluates on the FP32 pipe
                 "fp64_issued_frac": issued / fl.value,
                 "fp64_issued_flop_per_path_step": FP64_ISSUED_PER_PATH_STEP["flop"],
@@ -366,7 +366,7 @@ def run_ours(args):
                 # dram__bytes_read.sum + dram__bytes_write.sum of the path kernel per launch, from
                 # the same capture (code and constants only: it does not grow with the paths) --
                 # a profile figure, not a measurement of this run
-                "traffic": 340224, "traffic_source": NCU_PROFILE,
+                "traffic": 85504, "traffic_source": NCU_PROFILE,
                 "note": "achieved = 100 algorithmic FP64 flop per path-step (SURVEY 8d) x path-steps "
                         "of one GPU / mean path-kernel time (CUDA events); peak = DFMA peak measured "
                         "in this run (hexo_gpu_measure_fp64_peak; MEASURED_PEAKS.json has no FP64 "

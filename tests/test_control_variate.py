@@ -161,6 +161,47 @@ def _cv_worker(rank, world):
         dist.destroy_process_group()
 
 
+def test_distributed_geometric_sums_with_gloo(hexo_lib):
+    """world_size 2 over gloo with the geometric control's sums (5 n_opts doubles per rank)."""
+    import torch.multiprocessing as mp
+    mp.spawn(_geo_worker, args=(2,), nprocs=2, join=True)
+
+
+def _geo_worker(rank, world):
+    import os
+    import sys
+    import torch
+    import torch.distributed as dist
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path[:0] = [here, os.path.dirname(here)]
+    import oracle_api as oa
+    import hestonexotics_b200 as hx
+    from hestonexotics_b200 import pricing
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:29547", rank=rank, world_size=world)
+    try:
+        T, K, steps, n = [0.5, 1.0], [[100.0], [90.0, 110.0]], 12, 3001
+        c = oa.Contract(oa.ASIAN, T, K, steps)
+
+        def shard(rq, begin, count, world_, stats):
+            return torch.from_numpy(c.price_stream_geo(
+                int(rq.req.seed), int(rq.req.n_paths), int(rq.req.n_streams), begin, count,
+                normal_mode=oa.NORMAL_F64))
+        chains = [hx.OptionsChain.from_strikes(t, k) for t, k in zip(T, K)]
+        rq = pricing._Request(hx.HQEAnderson(hx.AAsianCallNonAdaptive),
+                              hx.HParams(*oa.DEFAULT_PARAMS), 100.0, chains, n, None, steps, 8,
+                              "f64", 29, control_variate="geometric")
+        res = pricing._reduce_shards(rq, shard)
+        full = c.price_stream_geo(8, n, 29, normal_mode=oa.NORMAL_F64)
+        np.testing.assert_allclose(res.sums, full, rtol=1e-12, atol=1e-9)
+        plain = pricing._Request(hx.HQEAnderson(hx.AAsianCallNonAdaptive),
+                                 hx.HParams(*oa.DEFAULT_PARAMS), 100.0, chains, n, None, steps, 8,
+                                 "f64", 29)
+        p0, se0 = pricing._finish(plain, full[:6])
+        assert np.all(np.abs(res.prices - p0) < 4 * se0 + 0.02) and np.all(res.stderr < se0)
+    finally:
+        dist.destroy_process_group()
+
+
 # --------------------------------------------------------------------------- GPU
 CV_CASES = [
     ("asian_chain", oa.ASIAN, [1.0], [[90.0, 100.0, 110.0]], 64, 3000, 96, 0, False),

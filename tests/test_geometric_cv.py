@@ -254,3 +254,60 @@ def test_gpu_geometric_control_cfg4_grid(gpu):
     cv = hx.price_full(ASIAN, P0, 100.0, ch, 2_000_000, 1, 1024, seed=5, control_variate="geometric")
     assert plain.stderr[0] / cv.stderr[0] > 20
     assert abs(cv.prices[0] - plain.prices[0]) < 4 * plain.stderr[0] + 0.005
+
+
+def _random_geo_contract(rng):
+    n_chains = int(rng.integers(1, 4))
+    T = np.cumsum(rng.uniform(0.05, 0.9, size=n_chains)).tolist()
+    S = float(rng.uniform(30.0, 300.0))
+    K = [sorted((S * rng.uniform(0.7, 1.3, size=int(rng.integers(1, 5)))).tolist())
+         for _ in range(n_chains)]
+    steps = int(rng.integers(2, 70))
+    params = (float(rng.uniform(0.01, 0.2)), float(rng.uniform(0.01, 0.2)),
+              float(rng.uniform(-0.95, 0.3)), float(rng.uniform(0.3, 6.0)),
+              float(rng.uniform(0.1, 1.2)))
+    n_paths = int(rng.integers(1, 1200))
+    return T, K, steps, params, S, n_paths, int(rng.integers(1, min(n_paths, 200) + 1))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("i", range(10))
+def test_gpu_geometric_sums_random_contracts(gpu, i):
+    """Seeded random Asian contracts (maturities, ragged chains, step counts, parameters, spot,
+    path / stream counts, both grids, both drifts): all five sums equal the oracle's, and the
+    host mean of the control is finite and below the forward."""
+    rng = np.random.default_rng(4000 + i)
+    T, K, steps, params, S, n_paths, n_streams = _random_geo_contract(rng)
+    exact, mart = bool(i & 1), bool(i & 2)
+    seed = int(rng.integers(0, 2 ** 62))
+    c = oa.Contract(oa.ASIAN, T, K, steps, params, S, drift_mode=int(mart))
+    want = c.price_stream_geo(seed, n_paths, n_streams, normal_mode=oa.NORMAL_F64, exact_grid=exact)
+    res = hx.price_full(ASIAN, hx.HParams(*params), S, chains_of(T, K), n_paths, None, steps,
+                        seed=seed, normal_mode="f64", n_streams=n_streams,
+                        time_grid="exact" if exact else "reference",
+                        drift="martingale" if mart else "reference", control_variate="geometric")
+    m = c.n_opts
+    floor = 1e-12 * n_paths * S
+    scale = np.concatenate([np.abs(want[:m]), np.abs(want[m:2 * m]), np.abs(want[m:2 * m]),
+                            np.abs(want[3 * m:4 * m]), np.abs(want[4 * m:])])
+    assert np.all(np.abs(res.sums - want) <= 1e-10 * scale + floor * np.repeat([1, S, S, 1, S], m))
+    eg = hx.geometric_asian_means(hx.HParams(*params), S, chains_of(T, K), steps,
+                                  "exact" if exact else "reference")
+    assert np.all(np.isfinite(eg)) and np.all(eg >= 0) and np.all(eg < S)
+    assert np.all(np.isfinite(res.prices)) and np.all(res.stderr >= 0)
+
+
+@pytest.mark.gpu
+def test_gpu_geometric_control_against_the_full_size_plain_estimate(gpu):
+    """Size-independent check on cfg4's grid: 10^7 paths WITH the control against 10^9 paths
+    without (the BASELINE job, 6 s).  The two estimators converge to limits that differ by the
+    part of the QE scheme's weak error the control removes; measured difference and errors are
+    printed, the bound is 5e-3 (0.1 % of the price)."""
+    ch = chains_of([1.0], [[100.0]])
+    plain = hx.price_full(ASIAN, P0, 100.0, ch, 1_000_000_000, 1, 1024, seed=1)
+    cv = hx.price_full(ASIAN, P0, 100.0, ch, 10_000_000, 1, 1024, seed=2, control_variate="geometric")
+    d = cv.prices[0] - plain.prices[0]
+    print(f"cfg4 grid: plain 1e9 paths {plain.prices[0]:.6f} +- {plain.stderr[0]:.6f}; geometric control "
+          f"1e7 paths {cv.prices[0]:.6f} +- {cv.stderr[0]:.6f}; difference {d:+.6f}")
+    assert cv.stderr[0] < 0.5 * plain.stderr[0]          # 100 x fewer paths, smaller error
+    assert abs(d) < 5e-3
