@@ -174,7 +174,8 @@ int geometric_asian_means(const hexo_price_request* r, const std::vector<SegCons
     }
     for (uint32_t j = j0; j < j1; ++j) {
       const double K = r->strikes[j];
-      out[j] = K > 0.0 ? F - sqrt(F * K) / M_PI * integral[j - j0] : F - K;
+      // (a call price: quadrature noise of 1e-9 must not make a far out-of-the-money one negative)
+      out[j] = K > 0.0 ? std::max(0.0, F - sqrt(F * K) / M_PI * integral[j - j0]) : F - K;
       if (!std::isfinite(out[j])) return HEXO_ERR_INVALID_ARGUMENT;  // degenerate transform
     }
   }

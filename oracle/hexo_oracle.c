@@ -358,7 +358,9 @@ static void accumulate_final_value(policy *o, const sde_state *s) {
     double log_interpolation = (s->log_X - s->prev_log_X) *
                                (o->earliest_unpriced_expi - s->prev_time) / o->init_step_size;
     /* the interpolation term has weights +x and -x: it does not change their sum */
-    o->final_log = (o->accumulated_log + log_interpolation) / o->accumulated_weight;
+    o->final_log = o->accumulated_weight > 0.0
+                       ? (o->accumulated_log + log_interpolation) / o->accumulated_weight
+                       : 0.0; /* one-step grid: no trapezoid was applied, G := 1 like the kernel */
   } else {
     o->final_value = s->prev_X + (s->cur_X - s->prev_X) *
                                      (o->earliest_unpriced_expi - s->prev_time) /
