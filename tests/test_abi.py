@@ -153,3 +153,31 @@ def test_types_mirror_reference():
     assert ex.tolist() == [0.5, 1.0] and off.tolist() == [0, 2, 3] and k.tolist() == [90.0, 110.0, 100.0]
     assert hx.shard_range(10, 0, 4) == (0, 3) and hx.shard_range(10, 3, 4) == (8, 2)
     assert sum(hx.shard_range(75776, r, 8)[1] for r in range(8)) == 75776
+
+
+def test_header_is_plain_c_and_links_from_c(tmp_path):
+    """The boundary is a C ABI: include/hexo_gpu.h compiles as strict C99 (no C++ types in the
+    signatures) and a C program links against the library and runs its host-only entry points
+    (ABI version, step schedule) -- the binding a C / cgo / JNI caller would make."""
+    import subprocess
+    src = tmp_path / "abi.c"
+    src.write_text(r"""
+#include <stdio.h>
+#include "hexo_gpu.h"
+int main(void) {
+  double expiries[2] = {0.5, 1.0};
+  hexo_segment seg[2];
+  if (hexo_gpu_abi_version() != HEXO_GPU_ABI_VERSION) return 1;
+  if (hexo_gpu_schedule(expiries, 2, 252, seg) != HEXO_OK) return 2;
+  printf("%u %u\n", seg[0].n_steps, seg[1].n_steps);
+  return 0;
+}
+""")
+    exe = tmp_path / "abi"
+    libdir = os.path.join(ROOT, "hestonexotics_b200", "lib")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror",
+                    "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                    "-L", libdir, "-lhexo_gpu", f"-Wl,-rpath,{libdir}"], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()
+    want = hx.schedule([0.5, 1.0], 252)
+    assert [int(x) for x in out] == [want[0][0], want[1][0]]
