@@ -51,6 +51,10 @@ constexpr int kInlineSegs = 8;     // maturities whose constants travel as kerne
 // the per-lane loop instead.
 constexpr int kTailListCap = 256;
 constexpr int kTailListBytes = 2 * kTailListCap;
+#ifndef HEXO_STEP_UNROLL
+#define HEXO_STEP_UNROLL 2  // the loop-carried rotation (Vold <- V <- V') needs an even count
+#endif
+constexpr int kStepUnroll = HEXO_STEP_UNROLL;
 #ifndef HEXO_TAIL_COOP
 #define HEXO_TAIL_COOP 1  // 0: every lane loops over its own tail draws (the round-1 scheme)
 #endif
@@ -624,7 +628,7 @@ heston_qe_paths_kernel(const __grid_constant__ PathArgs a) {
             }
             // unrolled by two so that the loop-carried rotation (Vold <- V <- V', Z_X) becomes
             // register renaming instead of moves
-#pragma unroll 2
+#pragma unroll kStepUnroll
             for (; m; --m, za += zstride) {
               double zv, zx;
               Ring::get(za, zv, zx);

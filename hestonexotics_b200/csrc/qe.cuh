@@ -62,6 +62,7 @@ struct QeVarMid {
   double m, s2h;  // :59, :60 (s^2/2)
   bool rare;      // psi >= 1.5 is POSSIBLE (decided on high words): qe_rare_exact() settles it, and
                   // then the quadratic value has to be replaced by qe_variance_rare
+  int hi_sw, hi_dm;  // high words of sqrt(w) and of m - sqrt(w): hi_sw < hi_dm proves psi >= 1.5
   double k0;      // MART only: K0* + (K1 + K3/2) V = -ln M of this step
 };
 
@@ -88,7 +89,9 @@ __device__ __forceinline__ double qe_variance_quad(const SegConst& g, const doub
   // word is larger" proves psi < 1.5; anything else, including equal high words (sw and dm within
   // 2^-20 of each other, one step in a million), goes to the rare block, where qe_rare_exact
   // takes the decision with the exact comparison.  No FP64 instruction for the test per step.
-  mid.rare = __double2hiint(sw) <= __double2hiint(dm);
+  mid.hi_sw = __double2hiint(sw);
+  mid.hi_dm = __double2hiint(dm);
+  mid.rare = mid.hi_sw <= mid.hi_dm;
   if (MART) {
     const double d = fma(-g.A2, dm, 1.0);                   // 1 - 2 A a
     const double k0 = fma(0.5, fast_log(d), -(g.A * sw) * fast_rcp(d));
@@ -102,6 +105,7 @@ __device__ __forceinline__ double qe_variance_quad(const SegConst& g, const doub
 // positive denormal counts as zero, where both branches are valid), for code that already sits
 // behind the cheap test mid.rare.
 __device__ __forceinline__ bool qe_rare_exact(const QeVarMid& mid) {
+  if (mid.hi_sw < mid.hi_dm) return true;  // clearly smaller: no FP64 needed (a NaN pair is equal)
   const double w = fma(mid.m, mid.m, -mid.s2h);
   return __double2hiint(fma(3.0, w, -mid.s2h)) <= 0;
 }
