@@ -46,6 +46,9 @@ FLOP_PER_PATH_STEP = 100.0  # SURVEY.md section 8(d), Asian
 # kernel's DRAM traffic per launch.  bench.py reports them next to the algorithmic figure.
 FP64_ISSUED_PER_PATH_STEP = {"instr": 41.19, "flop": 41.19 + 28.39}   # DFMA counts two flop
 NCU_PROFILE = "profiles/r02_path_kernel_ncu_keys.txt"
+# sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active of the path kernel per normal mode,
+# from the ncu captures in profiles/ (r02_path_kernel_ncu_keys{,_ppnd7,_f64}.txt)
+NCU_PIPE_FP64_PCT = {"f32": 37.0, "f32-ppnd7": 40.0, "f64": 63.2}
 WORKLOADS = {
     # name: (params, expiry, strikes, steps, paths, description)
     "cfg4": (PARAMS, EXPIRY, [STRIKE], STEPS, FULL_PATHS,
@@ -318,7 +321,10 @@ def run_ours(args):
                 continue
             m_total, m_kernel, m_sums, _, _, _ = timed_plan(mode, 1, 1, False)
             other_modes[mode] = {"value": path_steps / (m_total * 1e-3),
-                                 "price": float(m_sums[atm] / n_paths)}
+                                 "price": float(m_sums[atm] / n_paths),
+                                 "roofline_frac": FLOP_PER_PATH_STEP * path_steps / world /
+                                 (m_kernel * 1e-3) / fl.value,
+                                 "ncu_pipe_fp64_pct": NCU_PIPE_FP64_PCT[mode]}
 
     if rank == 0:
         this_gpu = path_steps / world / (kernel_ms * 1e-3)       # path-steps/s of one GPU
@@ -361,6 +367,7 @@ def run_ours(args):
                 "fp64_issued_frac": issued / fl.value,
                 "fp64_issued_flop_per_path_step": FP64_ISSUED_PER_PATH_STEP["flop"],
                 "fp64_instr_per_path_step": FP64_ISSUED_PER_PATH_STEP["instr"],
+                "ncu_pipe_fp64_pct": NCU_PIPE_FP64_PCT.get(args.normal_mode),
                 "ncu": "sm__inst_executed_pipe_fp64 and the instruction counts above are from the "
                        f"ncu capture of this kernel build, {NCU_PROFILE}",
                 # dram__bytes_read.sum + dram__bytes_write.sum of the path kernel per launch, from
@@ -378,7 +385,8 @@ def run_ours(args):
         if other_modes:
             out["other_normal_modes"] = {
                 "note": "the same job, one timed launch per mode; f32-ppnd7 = AS241's single-"
-                        "precision routine PPND7 (optional), f64 = PPND16 in double",
+                        "precision routine PPND7 (optional), f64 = PPND16 in double (all 100 "
+                        "algorithmic flop on the FP64 pipe); ncu_pipe_fp64_pct from profiles/",
                 **other_modes}
         if not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
