@@ -29,6 +29,7 @@ struct FmConst {
   double log_c[9];                     // 1/19, 1/17, ... 1/3: atanh series of fast_log
   double ln2_hi, ln2_lo;               // ln2 split so that e * ln2_hi is exact
   double em1[6];                       // (e^x - 1)/x on |x| <= 0.08: coefficients of x^6 .. x^1
+  double log1p_c[2];                   // -1/6, 1/5: the top of log1p's series in fast_neglog_tab
 };
 // static: one copy per translation unit (the kernels are built in several)
 static __constant__ FmConst kFm = {
@@ -47,6 +48,7 @@ static __constant__ FmConst kFm = {
     // one multiply-add fewer than the Taylor polynomial of the same accuracy (degree 7)
     {0.0001984435648549994893, 0.0013891666913593416117, 0.0083333332345585629478,
      0.041666665777675055694, 0.16666666666674568706, 0.50000000000071119961},
+    {-1.0 / 6.0, 0.2},
 };
 
 __device__ __forceinline__ double mufu_rcp64(double a) {
@@ -287,6 +289,28 @@ __device__ __forceinline__ double fast_log_ge1(double y) {
   p = fma(p, r, 1.0);
   const double ed = (double)e;
   return fma(ed, kFm.ln2_hi, fma(ed, kFm.ln2_lo, fma(r, p, t.lnc)));
+}
+
+// -ln(y) by the same algorithm for any normal y > 0 with the table in SHARED memory at byte
+// address `tab_saddr` (a copy of kLogTab): for code that all 32 lanes run with different table
+// indices, which the constant bank would serialise.  The negation rides on operand signs (no
+// instruction).  Absolute error <= 1.7e-16 max(1, |ln y|).
+__device__ __forceinline__ double fast_neglog_tab(double y, uint32_t tab_saddr) {
+  const int hi = __double2hiint(y);
+  const int ne = 1023 - (hi >> 20);
+  double invc, lnc;
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];"
+               : "=d"(invc), "=d"(lnc)
+               : "r"(tab_saddr + ((hi >> 9) & (127 << 4))));
+  const double f = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(y));
+  const double r = fma(f, invc, -1.0);
+  double p = fma(r, kFm.log1p_c[0], kFm.log1p_c[1]);  // -1/6, 1/5
+  p = fma(p, r, -0.25);
+  p = fma(p, r, kFm.log_c[8]);  // 1/3
+  p = fma(p, r, -0.5);
+  p = fma(p, r, 1.0);
+  const double ned = (double)ne;
+  return fma(ned, kFm.ln2_hi, fma(ned, kFm.ln2_lo, fma(-r, p, -lnc)));
 }
 
 __device__ __forceinline__ void exp_table_init(double* tab, int tid, int nthreads) {

@@ -201,11 +201,11 @@ normals_from_words_kernel(const uint64_t* __restrict__ words, double* __restrict
   using Ring = ZRing<NORMAL_MODE>;
   constexpr int kRing = ring_steps(NORMAL_MODE), kWords = 2 * kRing;
   const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5;
-  const uint32_t base = smem_addr(smem_raw);
-  const RingAddr ra = {base + 8 * tid, (uint32_t)(8 * T),
-                       base + 16 * kRing * T + Ring::kBytesPerStep * tid,
-                       (uint32_t)(Ring::kBytesPerStep * T),
-                       base + (16 + Ring::kBytesPerStep) * kRing * T + kTailListBytes * warp};
+  const RingAddr ra = ring_addr<NORMAL_MODE>(
+      smem_addr(smem_raw), tid, T,
+      smem_addr(smem_raw) + (uint32_t)ring_smem(T, NORMAL_MODE) + kTailListBytes * warp);
+  ring_logtab_init<NORMAL_MODE>(smem_raw, tid, T);
+  __syncthreads();
   const uint64_t chunk = (uint64_t)blockIdx.x * T + tid;
   WordSource src{chunk < n_chunks ? words + chunk * kWords : nullptr};
   uint64_t o[16];
@@ -1226,8 +1226,7 @@ int hexo_gpu_normals_from_words(const uint64_t* words_in, double* z_out, size_t 
   const size_t kw = 2 * (size_t)ring_steps(normal_mode);
   const size_t n_chunks = (n + kw - 1) / kw, padded = n_chunks * kw;
   const int block = kMaxBlock;
-  const size_t smem = (size_t)(16 + (normal_mode == HEXO_NORMAL_F64 ? 16 : 8)) *
-                          ring_steps(normal_mode) * block + (size_t)kTailListBytes * (block / 32);
+  const size_t smem = ring_smem(block, normal_mode) + (size_t)kTailListBytes * (block / 32);
   uint64_t* dw = nullptr;
   double* dz = nullptr;
   HEXO_CUDA(cudaMalloc(&dw, padded * 8));

@@ -102,12 +102,14 @@ __device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
 }
 
 // Phase 1 (F32 mode): the central formula for two draws at once (as241.f90:88-92).
-// tail0/tail1 are set when |q| > 0.425; such draws get their value from
-// normal_tail_f32 afterwards (z0/z1 then hold a finite placeholder).
+// rb0/rb1 return the bits of r = 0.180625 - q^2 (as241.f90:89): CONST1 = SPLIT1^2, so the draw
+// is outside the central region (|q| > 0.425, :88) exactly when r is negative, i.e. when the
+// sign bit of rb is set; such draws get their value from normal2_tail_mid_f32 afterwards
+// (z0/z1 then hold a finite placeholder).
 //   P7: AS241's single-precision routine PPND7 instead of PPND16's coefficients rounded to single
 template <bool P7 = false>
 __device__ __forceinline__ void normal2_central_f32(uint64_t w0, uint64_t w1, float& z0, float& z1,
-                                                    bool& tail0, bool& tail1) {
+                                                    uint32_t& rb0, uint32_t& rb1) {
   using P = Ppnd;
   const uint32_t hi0 = (uint32_t)(w0 >> 32), hi1 = (uint32_t)(w1 >> 32);
   // q = p - 1/2 from the high word of the draw
@@ -116,9 +118,10 @@ __device__ __forceinline__ void normal2_central_f32(uint64_t w0, uint64_t w1, fl
                             HEXO_BC(2.3283064365386963e-10f));  // 2^-32
   float q0, q1;
   unpack2(q2, q0, q1);
-  tail0 = fabsf(q0) > (float)P::SPLIT1;
-  tail1 = fabsf(q1) > (float)P::SPLIT1;
-  const uint64_t rc = pack2(fmaf(-q0, q0, (float)P::CONST1), fmaf(-q1, q1, (float)P::CONST1));
+  const float rr0 = fmaf(-q0, q0, (float)P::CONST1), rr1 = fmaf(-q1, q1, (float)P::CONST1);
+  rb0 = __float_as_uint(rr0);
+  rb1 = __float_as_uint(rr1);
+  const uint64_t rc = pack2(rr0, rr1);
   uint64_t num = P7 ? horner4x2(rc, Ppnd7::A3, Ppnd7::A2, Ppnd7::A1, Ppnd7::A0)
                     : horner8x2(rc, (float)P::A7, (float)P::A6, (float)P::A5, (float)P::A4,
                                 (float)P::A3, (float)P::A2, (float)P::A1, (float)P::A0);
@@ -182,29 +185,57 @@ static __device__ __noinline__ float normal_tail_far_f32(uint64_t w, float t) {
 
 // ---- double precision ---------------------------------------------------------
 
-// central region only; *tail is set when the draw needs the tail formula
-__device__ __forceinline__ double normal_central_f64(uint64_t w, bool& tail) {
+// central region only; rhi returns the high word of r = 0.180625 - q^2, whose sign bit says
+// that the draw needs the tail formula (|q| > 0.425 <=> r < 0)
+__device__ __forceinline__ double normal_central_f64(uint64_t w, uint32_t& rhi) {
   using P = Ppnd;
   const double q = u64_to_unit(w) - 0.5;
-  tail = fabs(q) > P::SPLIT1;
-  const double r = P::CONST1 - q * q;
+  const double r = fma(-q, q, P::CONST1);
+  rhi = (uint32_t)__double2hiint(r);
   return q * horner8<double>(r, P::A7, P::A6, P::A5, P::A4, P::A3, P::A2, P::A1, P::A0) *
          fast_rcp(horner8<double>(r, P::B7, P::B6, P::B5, P::B4, P::B3, P::B2, P::B1, 1.0));
 }
 
-// as241.f90:94-116 for a draw already known to be outside the central region: branch-free
-// intermediate tail (:104-109); *rr = sqrt(-ln(min(p,1-p))) tells the caller whether the far
-// tail (rr > 5) or the p in {0,1} case (rr not finite) has to replace the value.
-__device__ __forceinline__ double normal_tail_mid_f64(uint64_t w, double& rr) {
-  using P = Ppnd;
+// AS241's intermediate-tail coefficients (as241.f90:49-63) in the constant bank: there they are
+// free `c[3][..]` operands of DFMA; as literals every one of them costs two moves per use (a
+// double cannot be an immediate), 34 instructions per evaluation of the tail formula.
+struct PpndTailConst {
+  double c[8];  // C7 .. C0
+  double d[7];  // D7 .. D1
+  double const2;
+};
+static __constant__ PpndTailConst kPpndTail = {
+    {Ppnd::C7, Ppnd::C6, Ppnd::C5, Ppnd::C4, Ppnd::C3, Ppnd::C2, Ppnd::C1, Ppnd::C0},
+    {Ppnd::D7, Ppnd::D6, Ppnd::D5, Ppnd::D4, Ppnd::D3, Ppnd::D2, Ppnd::D1},
+    Ppnd::CONST2};
+
+// as241.f90:94-116 for a draw already known to be outside the central region (|q| > 0.425):
+// branch-free intermediate tail (:104-109); *rr = sqrt(-ln(min(p,1-p))) tells the caller whether
+// the far tail (rr >= 5) or the p in {0,1} case (rr ~ 26) has to replace the value.
+//   logtab: shared-space address of the block's logarithm table (fast_neglog_tab)
+// The sign of q = p - 1/2 is the top bit of the word (for |q| > 0.425 the rounding of RNG.cpp:31
+// cannot change it), so the selection of min(p, 1-p) (:94-98) and the final sign (:116) are
+// integer operations; v = 0 (p in {0, 1}) is lifted to the smallest normal double by an integer
+// max on its high word, which sends it to the far-tail path like any p < 1.4e-11.
+__device__ __forceinline__ double normal_tail_mid_f64(uint64_t w, double& rr, uint32_t logtab) {
   const double p = u64_to_unit(w);
-  const double q = p - 0.5;
-  const double v = (q < 0.0) ? p : 1.0 - p;
-  rr = fast_sqrt(-fast_log(fmax(v, 1e-300)));   // v == 0 -> rr ~ 26 -> far-tail path returns 0
-  const double r = rr - P::CONST2;
-  const double z = horner8<double>(r, P::C7, P::C6, P::C5, P::C4, P::C3, P::C2, P::C1, P::C0) *
-                   fast_rcp(horner8<double>(r, P::D7, P::D6, P::D5, P::D4, P::D3, P::D2, P::D1, 1.0));
-  return (q < 0.0) ? -z : z;
+  const double pc = 1.0 - p;
+  const bool upper = (int32_t)(w >> 32) < 0;  // q > 0
+  const int vhi = upper ? __double2hiint(pc) : __double2hiint(p);
+  const int vlo = upper ? __double2loint(pc) : __double2loint(p);
+  const double v = __hiloint2double(max(vhi, 0x00100000), vlo);
+  rr = fast_sqrt(fast_neglog_tab(v, logtab));
+  const double r = rr - kPpndTail.const2;
+  double num = fma(r, kPpndTail.c[0], kPpndTail.c[1]);
+  double den = fma(r, kPpndTail.d[0], kPpndTail.d[1]);
+#pragma unroll
+  for (int i = 2; i < 8; ++i) num = fma(num, r, kPpndTail.c[i]);
+#pragma unroll
+  for (int i = 2; i < 7; ++i) den = fma(den, r, kPpndTail.d[i]);
+  den = fma(den, r, 1.0);
+  const double z = num * fast_rcp(den);
+  // -z for q < 0: flip the sign bit where the word's top bit is clear
+  return __hiloint2double(__double2hiint(z) ^ (~(int)(w >> 32) & 0x80000000), __double2loint(z));
 }
 
 // far tail (:110-114) and p in {0,1} (:99-103) for the same draw (rare)
@@ -218,14 +249,6 @@ static __device__ __noinline__ double normal_tail_far_f64(uint64_t w, double rr)
   const double z = horner8<double>(r, P::E7, P::E6, P::E5, P::E4, P::E3, P::E2, P::E1, P::E0) /
                    horner8<double>(r, P::F7, P::F6, P::F5, P::F4, P::F3, P::F2, P::F1, 1.0);
   return (q < 0.0) ? -z : z;
-}
-
-// one draw, both tails
-__device__ __forceinline__ double normal_tail_f64(uint64_t w) {
-  double rr;
-  double z = normal_tail_mid_f64(w, rr);
-  if (rr > Ppnd::SPLIT2) z = normal_tail_far_f64(w, rr);
-  return z;
 }
 
 }  // namespace hexo

@@ -38,12 +38,25 @@ constexpr int kMaxBlock = 256;
 #endif
 constexpr int kMinBlocksPerSM = HEXO_MIN_BLOCKS;  // register budget: 65536 / (256 * this)
 constexpr int kStepsPerRound = 8;  // one shishua round = 16 words = 8 steps
-// Steps the default kernel transforms per refill.  F32 normals: two generator rounds -- the
-// per-lane tail loop then runs max-over-lanes(ceil(tails/2)) iterations for 32 draws instead of
-// twice that maximum for 16, and the refill overhead is paid half as often.  F64 normals keep one
-// round: their ring is twice as wide and two blocks per SM would not fit.
-__host__ __device__ constexpr int ring_steps(int normal_mode) {
-  return normal_mode == HEXO_NORMAL_F64 ? kStepsPerRound : 2 * kStepsPerRound;
+// Steps a thread transforms per refill: two generator rounds.  The tail phase then runs once per
+// 32 draws of a lane (154 +- 11 tail draws per warp, dealt out evenly over the lanes) and the
+// refill overhead is paid half as often as with one round.
+__host__ __device__ constexpr int ring_steps(int /*normal_mode*/) { return 2 * kStepsPerRound; }
+// Shared memory of a thread's ring per step.  F32 modes: the raw variance and spot words (two
+// planes of 8 bytes) and the pair (Z_V, Z_X) as float2.  F64 mode: the pair is a double2, so only
+// the variance words get a plane of their own (the psi >= 1.5 branch reads them); the spot word
+// of a TAIL draw waits in its own 8-byte z slot until the tail phase replaces it by the normal.
+// That keeps a 16-step ring at 24 bytes per step and thread in both cases: two blocks per SM.
+__host__ __device__ constexpr int ring_raw_planes(int normal_mode) {
+  return normal_mode == HEXO_NORMAL_F64 ? 1 : 2;
+}
+__host__ __device__ constexpr int ring_z_bytes(int normal_mode) {
+  return normal_mode == HEXO_NORMAL_F64 ? 16 : 8;
+}
+// F64 mode: the logarithm of the tail formula reads a 128-entry table (fast_log_tab) from shared
+// memory -- 32 lanes with 32 different indices would serialise on the constant bank
+__host__ __device__ constexpr int ring_logtab_bytes(int normal_mode) {
+  return normal_mode == HEXO_NORMAL_F64 ? 128 * 16 : 0;
 }
 constexpr int kInlineSegs = 8;     // maturities whose constants travel as kernel parameters
 // Entries of a warp's tail list (16 bits each).  A refill of 16 steps has 32 x 32 draws per
@@ -87,22 +100,26 @@ struct PathArgs {
                      // where shared-memory accumulators would cost occupancy)
 };
 
-// Shared memory of the path kernel (per block), T = threads, W = warps:
-//   wring  [2][R][T] the raw words of the R steps a refill covers (R = ring_steps), variance
-//                 words first, then spot words.  Kept because the tail phase of
+// Shared memory of the path kernel (per block), T = threads, W = warps, R = ring_steps:
+//   wring  [P][R][T] the raw words of the R steps a refill covers, P = ring_raw_planes: variance
+//                 words first, then (F32 modes) spot words.  Kept because the tail phase of
 //                 the normal transform re-reads them and because the psi >= 1.5
 //                 branch needs the UNIFORM of the variance draw (HSimulation.tpp:72)
-//   zring  [R][T] pairs (Z_V, Z_X) of the refill, float2 (F32 mode) / double2 (F64)
+//   zring  [R][T] pairs (Z_V, Z_X) of the refill, float2 (F32 modes) / double2 (F64)
+//   logtab [128]  F64 mode only: (1/c_i, ln c_i) of fast_log_tab
 //   exptab [32]   2^(j/32)
 //   fvbuf  [W][32] final values of a warp at a maturity
 //   tlist  [W][kTailListCap] 16-bit entries: the warp's tail draws of a refill (tail_phase_coop)
 //   acc    [W][n_acc] lane-owned payoff sums / sums of squares (/ control-variate sums)
+__host__ __device__ inline size_t ring_smem(int block, int normal_mode) {
+  return (size_t)(8 * ring_raw_planes(normal_mode) + ring_z_bytes(normal_mode)) *
+             ring_steps(normal_mode) * block +
+         ring_logtab_bytes(normal_mode);
+}
 __host__ __device__ inline size_t path_kernel_smem(int block, uint32_t n_acc, int normal_mode,
                                                    bool acc_in_smem = true) {
   const int warps = block / 32;
-  const size_t steps = ring_steps(normal_mode);
-  const size_t zbytes = (normal_mode == HEXO_NORMAL_F64 ? 16 : 8) * steps * block;
-  return zbytes + (size_t)16 * steps * block + 32 * 8 + (size_t)32 * 8 * warps +
+  return ring_smem(block, normal_mode) + 32 * 8 + (size_t)32 * 8 * warps +
          (size_t)kTailListBytes * warps + (acc_in_smem ? (size_t)warps * n_acc * 8 : 0);
 }
 
@@ -164,25 +181,57 @@ __device__ __forceinline__ uint32_t bfind32(uint32_t x) {
 __device__ __forceinline__ void sts_u16(uint32_t addr, uint32_t v) {
   asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((unsigned short)v));
 }
+__device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
+  unsigned short v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
+  return v;
+}
 __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
   uint32_t v;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
   return v;
 }
 
-// Shared-memory ring of one thread (addresses in the shared window).  Raw words live in two
-// planes [variance words | spot words] of RING steps each, so word j of a refill (j = RING d +
-// step, d = 0 variance / 1 spot) sits at ucol + j ustride; the (Z_V, Z_X) pair of step s sits at
-// zcol + s zstride.  Lane l of a warp owns column l: ucol = (lane 0's ucol) + 8 l.
+// Shared-memory ring of one thread (addresses in the shared window).  Raw words live in planes
+// [variance words | spot words] of RING steps each, so word j of a refill (j = RING d + step,
+// d = 0 variance / 1 spot) sits at ucol + j ustride; the (Z_V, Z_X) pair of step s sits at
+// zcol + s zstride.  Lane l of a warp owns column l: ucol = (lane 0's ucol) + 8 l.  (F64 mode has
+// no spot plane: the spot word of a tail draw sits in the second half of its step's z pair.)
 struct RingAddr {
   uint32_t ucol, ustride, zcol, zstride;
-  uint32_t tlist;  // this warp's tail list (kTailListBytes), see tail_phase_coop
+  uint32_t tlist;   // this warp's tail list (kTailListBytes), see tail_phase_coop
+  uint32_t logtab;  // F64 mode: the block's table of fast_log_tab
 };
+// carves the ring out of the block's dynamic shared memory at `base` (ring_smem bytes)
+template <int NORMAL_MODE>
+__device__ __forceinline__ RingAddr ring_addr(uint32_t base, int tid, int T, uint32_t tlist) {
+  constexpr uint32_t kP = ring_raw_planes(NORMAL_MODE), kZ = ring_z_bytes(NORMAL_MODE);
+  constexpr uint32_t kR = ring_steps(NORMAL_MODE);
+  RingAddr ra;
+  ra.ucol = base + 8 * tid;
+  ra.ustride = 8 * T;
+  ra.zcol = base + 8 * kP * kR * T + kZ * tid;
+  ra.zstride = kZ * T;
+  ra.tlist = tlist;
+  ra.logtab = base + (8 * kP + kZ) * kR * T;
+  return ra;
+}
+// fills the logarithm table of the F64 tail formula (no-op in the F32 modes); the block must
+// synchronise before the first refill
+template <int NORMAL_MODE>
+__device__ __forceinline__ void ring_logtab_init(unsigned char* smem_base, int tid, int T) {
+  if (ring_logtab_bytes(NORMAL_MODE) == 0) return;
+  constexpr size_t kOff = (size_t)(8 * ring_raw_planes(NORMAL_MODE) + ring_z_bytes(NORMAL_MODE)) *
+                          ring_steps(NORMAL_MODE);
+  LogTabEntry* tab = reinterpret_cast<LogTabEntry*>(smem_base + kOff * T);
+  for (int j = tid; j < 128; j += T) tab[j] = kLogTab[j];
+}
 
 // Raw words -> normals in two phases (normals.cuh): the central formula for all draws of a
 // generator round, then the tail draws of the whole refill.
-//   central_round_planar : one generator round (8 steps), returns its tail bits; tail bit j
-//                          marks word j of the refill
+//   central_round_planar : one generator round (8 steps); shifts the draws' tail flags into two
+//                          accumulators (ring_refill turns them into the mask whose bit j
+//                          marks word j of the refill)
 //   tail_phase_planar    : every lane loops over its OWN tail draws, two per iteration
 //   tail_pair            : two tail draws -> their slots of the z ring
 template <int NORMAL_MODE>
@@ -191,22 +240,24 @@ struct ZRing;
 template <bool P7>
 struct ZRingF32 {
   static constexpr int kBytesPerStep = 8;  // float2 (Z_V, Z_X)
-  template <int RING>
-  static __device__ __forceinline__ uint32_t central_round_planar(const uint64_t (&o)[16],
-                                                                  int step0, uint32_t zcol,
-                                                                  uint32_t zstride) {
-    static_assert(2 * RING <= 32 && (RING & (RING - 1)) == 0, "tail mask is 32 bits");
-    uint32_t tails = 0;
+  static constexpr int kRawPlanes = 2;     // variance and spot words
+  static constexpr bool kTailPairs = true; // the tail formula takes two draws per packed chain
+  // One generator round.  The tail flag of a draw is the SIGN BIT of its r = 0.180625 - q^2
+  // (CONST1 = SPLIT1^2, as241.f90:20-21,88-89): each flag is shifted into an accumulator with one
+  // funnel shift (no compare, no select); `tv` collects the variance draws' flags, `tx` the spot
+  // draws', in step order -- tail_mask() turns the two into the mask the tail phase reads.
+  static __device__ __forceinline__ void central_round_planar(const uint64_t (&o)[16], int step0,
+                                                              uint32_t zcol, uint32_t zstride,
+                                                              uint32_t& tv, uint32_t& tx) {
 #pragma unroll
     for (int s = 0; s < kStepsPerRound; ++s) {
       float zv, zx;
-      bool t0, t1;
-      normal2_central_f32<P7>(o[2 * s], o[2 * s + 1], zv, zx, t0, t1);
+      uint32_t r0, r1;
+      normal2_central_f32<P7>(o[2 * s], o[2 * s + 1], zv, zx, r0, r1);
       sts_b64(zcol + (step0 + s) * zstride, pack2(zv, zx));
-      if (t0) tails |= 1u << (step0 + s);
-      if (t1) tails |= 1u << (RING + step0 + s);
+      tv = __funnelshift_l(r0, tv, 1);
+      tx = __funnelshift_l(r1, tx, 1);
     }
-    return tails;
   }
   // two tail draws (words w0, w1; `two` false: w1 is w0 again) -> z ring slots za0, za1
   static __device__ __forceinline__ void tail_pair(uint64_t w0, uint64_t w1, bool two, uint32_t za0,
@@ -235,71 +286,89 @@ struct ZRing<HEXO_NORMAL_F32_PPND7> : ZRingF32<true> {};
 
 template <>
 struct ZRing<HEXO_NORMAL_F64> {
-  static constexpr int kBytesPerStep = 16;  // double2 (Z_V, Z_X)
-  template <int RING>
-  static __device__ __forceinline__ uint32_t central_round_planar(const uint64_t (&o)[16],
-                                                                  int step0, uint32_t zcol,
-                                                                  uint32_t zstride) {
-    static_assert(2 * RING <= 32 && (RING & (RING - 1)) == 0, "tail mask is 32 bits");
-    uint32_t tails = 0;
+  static constexpr int kBytesPerStep = 16;   // double2 (Z_V, Z_X)
+  static constexpr int kRawPlanes = 1;       // variance words only, see ring_raw_planes
+  static constexpr bool kTailPairs = false;  // one tail draw per lane and iteration
+  static __device__ __forceinline__ void central_round_planar(const uint64_t (&o)[16], int step0,
+                                                              uint32_t zcol, uint32_t zstride,
+                                                              uint32_t& tv, uint32_t& tx) {
 #pragma unroll
     for (int s = 0; s < kStepsPerRound; ++s) {
-      bool t0, t1;
-      const double zv = normal_central_f64(o[2 * s], t0);
-      const double zx = normal_central_f64(o[2 * s + 1], t1);
-      sts_f64x2(zcol + (step0 + s) * zstride, zv, zx);
-      if (t0) tails |= 1u << (step0 + s);
-      if (t1) tails |= 1u << (RING + step0 + s);
+      uint32_t r0, r1;  // high words of r = 0.180625 - q^2: the sign bit is the tail flag
+      const double zv = normal_central_f64(o[2 * s], r0);
+      const double zx = normal_central_f64(o[2 * s + 1], r1);
+      const uint32_t za = zcol + (step0 + s) * zstride;
+      sts_f64x2(za, zv, zx);
+      // a spot draw outside the central region: park its raw word where its normal will go
+      if ((int32_t)r1 < 0) sts_b64(za + 8, o[2 * s + 1]);
+      tv = __funnelshift_l(r0, tv, 1);
+      tx = __funnelshift_l(r1, tx, 1);
     }
-    return tails;
   }
-  static __device__ __forceinline__ void tail_pair(uint64_t w0, uint64_t w1, bool two, uint32_t za0,
-                                                   uint32_t za1) {
-    double r0, r1;
-    double z0 = normal_tail_mid_f64(w0, r0), z1 = normal_tail_mid_f64(w1, r1);
-    if (fmax(r0, r1) > Ppnd::SPLIT2) {  // far tail: essentially never
-      if (r0 > Ppnd::SPLIT2) z0 = normal_tail_far_f64(w0, r0);
-      if (r1 > Ppnd::SPLIT2) z1 = normal_tail_far_f64(w1, r1);
-    }
-    sts_f64(za0, z0);
-    if (two) sts_f64(za1, z1);
+  // one tail draw (word w) -> its z ring slot
+  static __device__ __forceinline__ void tail_one(uint64_t w, uint32_t za, uint32_t logtab) {
+    double r;
+    double z = normal_tail_mid_f64(w, r, logtab);
+    // far tail (r > 5, as241.f90:105): essentially never.  Tested on the high word of r (5.0 is
+    // 0x40140000:00000000; at r = 5 itself the two formulas agree to the algorithm's 1e-16)
+    if (__double2hiint(r) >= 0x40140000) z = normal_tail_far_f64(w, r);
+    sts_f64(za, z);
   }
   static __device__ __forceinline__ void get(uint32_t addr, double& zv, double& zx) {
     lds_f64x2(addr, zv, zx);
   }
 };
 
-// Tail phase, per lane: each lane loops over its own tail draws, two per iteration (independent
-// evaluations hide the MUFU latencies).  The warp runs as long as its unluckiest lane.
+// Where word j of a lane's refill and its normal live (zcol / ucol: that lane's columns).
+template <int NORMAL_MODE, int RING>
+__device__ __forceinline__ uint32_t tail_z_addr(uint32_t zcol, uint32_t zstride, uint32_t j) {
+  constexpr int kLog = RING == 16 ? 4 : RING == 8 ? 3 : RING == 4 ? 2 : 1;
+  constexpr uint32_t kHalf = ZRing<NORMAL_MODE>::kBytesPerStep / 2;
+  return zcol + (j & (RING - 1)) * zstride + (j >> kLog) * kHalf;
+}
+template <int NORMAL_MODE, int RING>
+__device__ __forceinline__ uint32_t tail_word_addr(uint32_t ucol, uint32_t ustride, uint32_t zaddr,
+                                                   uint32_t j) {
+  if (ZRing<NORMAL_MODE>::kRawPlanes == 2) return ucol + j * ustride;
+  return j < (uint32_t)RING ? ucol + j * ustride : zaddr;  // F64: a spot word waits in its z slot
+}
+
+// Tail phase, per lane: each lane loops over its own tail draws (F32 modes: two per iteration,
+// independent evaluations hide the MUFU latencies).  The warp runs as long as its unluckiest lane.
 template <int NORMAL_MODE, int RING>
 __device__ __forceinline__ void tail_phase_planar(uint32_t tails, const RingAddr& ra) {
   using Ring = ZRing<NORMAL_MODE>;
-  constexpr int kLog = RING == 16 ? 4 : RING == 8 ? 3 : RING == 4 ? 2 : 1;
-  constexpr uint32_t kHalf = Ring::kBytesPerStep / 2;
   while (tails) {
     const uint32_t j0 = bfind32(tails);
     const uint32_t b0 = 1u << j0, rest = tails ^ b0;
-    const bool two = rest != 0;
-    const uint32_t j1 = bfind32(two ? rest : b0);  // j0 again when it was the last one
-    tails = rest & ~(1u << j1);
-    const uint64_t w0 = lds_b64(ra.ucol + j0 * ra.ustride);
-    const uint64_t w1 = lds_b64(ra.ucol + j1 * ra.ustride);
-    Ring::tail_pair(w0, w1, two, ra.zcol + (j0 & (RING - 1)) * ra.zstride + (j0 >> kLog) * kHalf,
-                    ra.zcol + (j1 & (RING - 1)) * ra.zstride + (j1 >> kLog) * kHalf);
+    const uint32_t za0 = tail_z_addr<NORMAL_MODE, RING>(ra.zcol, ra.zstride, j0);
+    const uint64_t w0 = lds_b64(tail_word_addr<NORMAL_MODE, RING>(ra.ucol, ra.ustride, za0, j0));
+    if constexpr (Ring::kTailPairs) {
+      const bool two = rest != 0;
+      const uint32_t j1 = bfind32(two ? rest : b0);  // j0 again when it was the last one
+      tails = rest & ~(1u << j1);
+      const uint32_t za1 = tail_z_addr<NORMAL_MODE, RING>(ra.zcol, ra.zstride, j1);
+      const uint64_t w1 = lds_b64(tail_word_addr<NORMAL_MODE, RING>(ra.ucol, ra.ustride, za1, j1));
+      Ring::tail_pair(w0, w1, two, za0, za1);
+    } else {
+      tails = rest;
+      Ring::tail_one(w0, za0, ra.logtab);
+    }
   }
 }
 
 // Tail phase, warp-cooperative: the tail draws of all 32 lanes (154 +- 11 of the 1024 draws of a
-// 16-step refill) are listed in shared memory and dealt out evenly, so the warp runs
-// ceil(total / 64) two-draw iterations (3) instead of as many as its unluckiest lane needs (4.8
-// on average).  All 32 lanes of the warp must call this together.
+// 16-step refill) are listed in shared memory and dealt out evenly.  F32 modes: two draws per
+// lane and iteration, ceil(total / 64) = 3 iterations instead of as many as the unluckiest lane
+// needs (4.8 on average).  F64 mode: one draw per lane and iteration, ceil(total / 32) = 5
+// iterations of half the length (96 % of the lane slots do work; with two draws per iteration it
+// would be 80 %).  All 32 lanes of the warp must call this together.
 //   list entry = (owner lane << 5) | word index j, 16 bits; lane l takes entries [l c, l c + c),
-//   c = 2 ceil(total / 64), so that lanes working side by side read different owners' columns
+//   c = entries per lane, so that lanes working side by side read different owners' columns
 template <int NORMAL_MODE, int RING>
 __device__ __forceinline__ void tail_phase_coop(uint32_t tails, const RingAddr& ra, uint32_t lane) {
   using Ring = ZRing<NORMAL_MODE>;
-  constexpr int kLog = RING == 16 ? 4 : RING == 8 ? 3 : RING == 4 ? 2 : 1;
-  constexpr uint32_t kHalf = Ring::kBytesPerStep / 2;
+  constexpr uint32_t kB = Ring::kBytesPerStep;
   const uint32_t cnt = __popc(tails);
   uint32_t incl = cnt;  // inclusive prefix sum of the lanes' counts
 #pragma unroll
@@ -321,22 +390,37 @@ __device__ __forceinline__ void tail_phase_coop(uint32_t tails, const RingAddr& 
     la += 2;
   }
   __syncwarp();
-  const uint32_t c = ((total + 63) >> 6) << 1;
-  const uint32_t ubase = ra.ucol - 8 * lane, zbase = ra.zcol - Ring::kBytesPerStep * lane;
-  uint32_t i = lane * c;
-  for (uint32_t t = 0; t < c; t += 2, i += 2) {
-    if (i < total) {
-      const uint32_t e2 = lds_u32(ra.tlist + 2 * i);
-      const bool two = i + 1 < total;
-      const uint32_t e0 = e2 & 0xffffu, e1 = two ? e2 >> 16 : e0;
-      const uint32_t l0 = e0 >> 5, j0 = e0 & 31u, l1 = e1 >> 5, j1 = e1 & 31u;
-      const uint64_t w0 = lds_b64(ubase + 8 * l0 + j0 * ra.ustride);
-      const uint64_t w1 = lds_b64(ubase + 8 * l1 + j1 * ra.ustride);
-      Ring::tail_pair(w0, w1, two,
-                      zbase + Ring::kBytesPerStep * l0 + (j0 & (RING - 1)) * ra.zstride +
-                          (j0 >> kLog) * kHalf,
-                      zbase + Ring::kBytesPerStep * l1 + (j1 & (RING - 1)) * ra.zstride +
-                          (j1 >> kLog) * kHalf);
+  const uint32_t ubase = ra.ucol - 8 * lane, zbase = ra.zcol - kB * lane;
+  if constexpr (Ring::kTailPairs) {
+    const uint32_t c = ((total + 63) >> 6) << 1;
+    uint32_t i = lane * c;
+    for (uint32_t t = 0; t < c; t += 2, i += 2) {
+      if (i < total) {
+        const uint32_t e2 = lds_u32(ra.tlist + 2 * i);
+        const bool two = i + 1 < total;
+        const uint32_t e0 = e2 & 0xffffu, e1 = two ? e2 >> 16 : e0;
+        const uint32_t l0 = e0 >> 5, j0 = e0 & 31u, l1 = e1 >> 5, j1 = e1 & 31u;
+        const uint32_t za0 = tail_z_addr<NORMAL_MODE, RING>(zbase + kB * l0, ra.zstride, j0);
+        const uint32_t za1 = tail_z_addr<NORMAL_MODE, RING>(zbase + kB * l1, ra.zstride, j1);
+        const uint64_t w0 =
+            lds_b64(tail_word_addr<NORMAL_MODE, RING>(ubase + 8 * l0, ra.ustride, za0, j0));
+        const uint64_t w1 =
+            lds_b64(tail_word_addr<NORMAL_MODE, RING>(ubase + 8 * l1, ra.ustride, za1, j1));
+        Ring::tail_pair(w0, w1, two, za0, za1);
+      }
+    }
+  } else {
+    const uint32_t c = (total + 31) >> 5;
+    uint32_t i = lane * c;
+    for (uint32_t t = 0; t < c; ++t, ++i) {
+      if (i < total) {
+        const uint32_t e = lds_u16(ra.tlist + 2 * i);
+        const uint32_t l0 = e >> 5, j0 = e & 31u;
+        const uint32_t za0 = tail_z_addr<NORMAL_MODE, RING>(zbase + kB * l0, ra.zstride, j0);
+        const uint64_t w0 =
+            lds_b64(tail_word_addr<NORMAL_MODE, RING>(ubase + 8 * l0, ra.ustride, za0, j0));
+        Ring::tail_one(w0, za0, ra.logtab);
+      }
     }
   }
   __syncwarp();
@@ -352,7 +436,7 @@ __device__ __forceinline__ void ring_refill(Gen& rng, uint64_t (&o)[16], bool ha
   using Ring = ZRing<NORMAL_MODE>;
   constexpr int kRing = ring_steps(NORMAL_MODE);
   const uint32_t uplane = kRing * ra.ustride;
-  uint32_t tails = 0;
+  uint32_t tv = 0, tx = 0;
 #pragma unroll
   for (int r = 0; r < kRing / kStepsPerRound; ++r) {
     if (r > 0 || !have_first) rng.round(o);
@@ -360,10 +444,13 @@ __device__ __forceinline__ void ring_refill(Gen& rng, uint64_t (&o)[16], bool ha
 #pragma unroll
     for (int s = 0; s < kStepsPerRound; ++s) {
       sts_b64(u0 + s * ra.ustride, o[2 * s]);
-      sts_b64(u0 + s * ra.ustride + uplane, o[2 * s + 1]);
+      if (Ring::kRawPlanes == 2) sts_b64(u0 + s * ra.ustride + uplane, o[2 * s + 1]);
     }
-    tails |= Ring::template central_round_planar<kRing>(o, r * kStepsPerRound, ra.zcol, ra.zstride);
+    Ring::central_round_planar(o, r * kStepsPerRound, ra.zcol, ra.zstride, tv, tx);
   }
+  // After kRing shifts the flag of step s sits at bit kRing - 1 - s of its accumulator; the tail
+  // phase wants bit j = word index (variance word of step s: j = s, spot word: j = kRing + s).
+  const uint32_t tails = __brev((tv << (32 - kRing)) | (tx << (32 - 2 * kRing)));
 #if HEXO_TAIL_COOP
   tail_phase_coop<NORMAL_MODE, kRing>(tails, ra, lane);
 #else
@@ -464,15 +551,17 @@ heston_qe_paths_kernel(const __grid_constant__ PathArgs a) {
   unsigned char* sp = smem_raw;
   // pin32: keep the ring addresses in registers; otherwise ptxas re-derives them from
   // %tid / %ntid / the shared window base inside the step and tail loops (~20 instructions)
-  // raw words in two planes, [variance words | spot words], each [kRing][T]: the two 64-bit
+  // raw words in planes, [variance words | spot words], each [kRing][T]: the two 64-bit
   // stores of a step are not adjacent (adjacent, ptxas fuses them into one 128-bit store and
   // pays four moves to line the words up in an aligned register quad) and a warp's 64-bit
   // accesses touch consecutive 8-byte slots
-  const uint32_t zstride = pin32(Ring::kBytesPerStep * T), ustride = pin32(8 * T);
-  const uint32_t ucol = pin32(smem_addr(sp) + 8 * tid);  // variance word of step 0
-  sp += (size_t)16 * kRing * T;
-  const uint32_t zcol = pin32(smem_addr(sp) + Ring::kBytesPerStep * tid);
-  sp += (size_t)Ring::kBytesPerStep * kRing * T;
+  const RingAddr ra0 = ring_addr<NORMAL_MODE>(smem_addr(sp), tid, T, 0);
+  const uint32_t zstride = pin32(ra0.zstride), ustride = pin32(ra0.ustride);
+  const uint32_t ucol = pin32(ra0.ucol);  // variance word of step 0
+  const uint32_t zcol = pin32(ra0.zcol);
+  const uint32_t logtab = ring_logtab_bytes(NORMAL_MODE) ? pin32(ra0.logtab) : 0u;
+  ring_logtab_init<NORMAL_MODE>(sp, tid, T);
+  sp += ring_smem(T, NORMAL_MODE);
   double* exptab = reinterpret_cast<double*>(sp);
   const uint32_t exptab_s = pin32(smem_addr(sp));
   sp += 32 * 8;
@@ -515,7 +604,8 @@ heston_qe_paths_kernel(const __grid_constant__ PathArgs a) {
           : 0u;
 
   Gen rng;  // Shishua (the reference's generator) or PhiloxGen (optional counter mode)
-  const RingAddr ra = {ucol, ustride, zcol, zstride, tlist};
+  const RingAddr ra = {ucol, ustride, zcol, zstride, tlist, logtab};
+  if (ring_logtab_bytes(NORMAL_MODE)) __syncthreads();  // logtab: the first refill reads it
   {
     uint64_t o[16];
     rng.init(a.seed, sid, 0, 0, o);
