@@ -185,15 +185,25 @@ static __device__ __noinline__ float normal_tail_far_f32(uint64_t w, float t) {
 
 // ---- double precision ---------------------------------------------------------
 
-// central region only; rhi returns the high word of r = 0.180625 - q^2, whose sign bit says
-// that the draw needs the tail formula (|q| > 0.425 <=> r < 0)
-__device__ __forceinline__ double normal_central_f64(uint64_t w, uint32_t& rhi) {
+// Central formula (as241.f90:88-92) for the two draws of a step at once: z = q A(r) / B(r) with
+// ONE reciprocal for both -- 1 / (B_v B_x), then times the other draw's B -- which trades a MUFU
+// seed (and the move that zeroes its low word) for two multiplications it saves elsewhere.
+// rhi0 / rhi1 return the high words of r = 0.180625 - q^2, whose sign bit says that the draw
+// needs the tail formula (|q| > 0.425 <=> r < 0); such draws get a finite placeholder here.
+__device__ __forceinline__ void normal2_central_f64(uint64_t w0, uint64_t w1, double& z0, double& z1,
+                                                    uint32_t& rhi0, uint32_t& rhi1) {
   using P = Ppnd;
-  const double q = u64_to_unit(w) - 0.5;
-  const double r = fma(-q, q, P::CONST1);
-  rhi = (uint32_t)__double2hiint(r);
-  return q * horner8<double>(r, P::A7, P::A6, P::A5, P::A4, P::A3, P::A2, P::A1, P::A0) *
-         fast_rcp(horner8<double>(r, P::B7, P::B6, P::B5, P::B4, P::B3, P::B2, P::B1, 1.0));
+  const double q0 = u64_to_unit(w0) - 0.5, q1 = u64_to_unit(w1) - 0.5;
+  const double r0 = fma(-q0, q0, P::CONST1), r1 = fma(-q1, q1, P::CONST1);
+  rhi0 = (uint32_t)__double2hiint(r0);
+  rhi1 = (uint32_t)__double2hiint(r1);
+  const double n0 = q0 * horner8<double>(r0, P::A7, P::A6, P::A5, P::A4, P::A3, P::A2, P::A1, P::A0);
+  const double n1 = q1 * horner8<double>(r1, P::A7, P::A6, P::A5, P::A4, P::A3, P::A2, P::A1, P::A0);
+  const double d0 = horner8<double>(r0, P::B7, P::B6, P::B5, P::B4, P::B3, P::B2, P::B1, 1.0);
+  const double d1 = horner8<double>(r1, P::B7, P::B6, P::B5, P::B4, P::B3, P::B2, P::B1, 1.0);
+  const double y = fast_rcp(d0 * d1);  // 0.0021 < B < 100 for every |q| <= 1/2, tail draws included
+  z0 = n0 * (y * d1);
+  z1 = n1 * (y * d0);
 }
 
 // AS241's intermediate-tail coefficients (as241.f90:49-63) in the constant bank: there they are

@@ -200,7 +200,9 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
 struct RingAddr {
   uint32_t ucol, ustride, zcol, zstride;
   uint32_t tlist;   // this warp's tail list (kTailListBytes), see tail_phase_coop
-  uint32_t logtab;  // F64 mode: the block's table of fast_log_tab
+  uint32_t logtab;  // F64 mode: the block's table of fast_neglog_tab
+  uint32_t ublock, zblock;  // thread 0's ucol / zcol (block-uniform: they can live in uniform
+                            // registers, which costs the tail loop nothing)
 };
 // carves the ring out of the block's dynamic shared memory at `base` (ring_smem bytes)
 template <int NORMAL_MODE>
@@ -214,6 +216,8 @@ __device__ __forceinline__ RingAddr ring_addr(uint32_t base, int tid, int T, uin
   ra.zstride = kZ * T;
   ra.tlist = tlist;
   ra.logtab = base + (8 * kP + kZ) * kR * T;
+  ra.ublock = base;
+  ra.zblock = base + 8 * kP * kR * T;
   return ra;
 }
 // fills the logarithm table of the F64 tail formula (no-op in the F32 modes); the block must
@@ -295,8 +299,8 @@ struct ZRing<HEXO_NORMAL_F64> {
 #pragma unroll
     for (int s = 0; s < kStepsPerRound; ++s) {
       uint32_t r0, r1;  // high words of r = 0.180625 - q^2: the sign bit is the tail flag
-      const double zv = normal_central_f64(o[2 * s], r0);
-      const double zx = normal_central_f64(o[2 * s + 1], r1);
+      double zv, zx;
+      normal2_central_f64(o[2 * s], o[2 * s + 1], zv, zx, r0, r1);
       const uint32_t za = zcol + (step0 + s) * zstride;
       sts_f64x2(za, zv, zx);
       // a spot draw outside the central region: park its raw word where its normal will go
@@ -382,16 +386,16 @@ __device__ __forceinline__ void tail_phase_coop(uint32_t tails, const RingAddr& 
     return;
   }
   uint32_t la = ra.tlist + 2 * (incl - cnt);
-  const uint32_t tag = lane << 5;
-  while (tails) {
-    const uint32_t j = bfind32(tails);
-    tails ^= 1u << j;
-    sts_u16(la, tag | j);
-    la += 2;
-  }
-  __syncwarp();
-  const uint32_t ubase = ra.ucol - 8 * lane, zbase = ra.zcol - kB * lane;
+  const uint32_t ubase = ra.ucol - 8 * lane, zbase = ra.zcol - kB * lane;  // lane 0's columns
   if constexpr (Ring::kTailPairs) {
+    const uint32_t tag = lane << 5;
+    while (tails) {
+      const uint32_t j = bfind32(tails);
+      tails ^= 1u << j;
+      sts_u16(la, tag | j);
+      la += 2;
+    }
+    __syncwarp();
     const uint32_t c = ((total + 63) >> 6) << 1;
     uint32_t i = lane * c;
     for (uint32_t t = 0; t < c; t += 2, i += 2) {
@@ -410,16 +414,30 @@ __device__ __forceinline__ void tail_phase_coop(uint32_t tails, const RingAddr& 
       }
     }
   } else {
+    // F64 mode.  Entry = (z slot of the draw - zblock) / 8 = 2 owner thread + 2 T (j mod RING) +
+    // (j div RING): the z slot is zblock + 8 entry; an odd entry is a spot draw, whose raw word
+    // waits in that very slot, an even one a variance draw with its word at ublock + 4 entry (the
+    // variance plane has half the z ring's pitch).  Five instructions of decoding per draw.
+    static_assert(kB == 16, "entry arithmetic of the F64 ring");
+    const uint32_t t2 = ra.zstride >> 3, tag = (ra.zcol - ra.zblock) >> 3;
+    const uint32_t spotfix = RING * t2 - 1;  // entry(j) = tag + j t2 - (j div RING) spotfix
+    while (tails) {
+      const uint32_t j = bfind32(tails);
+      tails ^= 1u << j;
+      uint32_t e = j * t2 + tag;
+      if (j >= (uint32_t)RING) e -= spotfix;
+      sts_u16(la, e);
+      la += 2;
+    }
+    __syncwarp();
     const uint32_t c = (total + 31) >> 5;
     uint32_t i = lane * c;
     for (uint32_t t = 0; t < c; ++t, ++i) {
       if (i < total) {
         const uint32_t e = lds_u16(ra.tlist + 2 * i);
-        const uint32_t l0 = e >> 5, j0 = e & 31u;
-        const uint32_t za0 = tail_z_addr<NORMAL_MODE, RING>(zbase + kB * l0, ra.zstride, j0);
-        const uint64_t w0 =
-            lds_b64(tail_word_addr<NORMAL_MODE, RING>(ubase + 8 * l0, ra.ustride, za0, j0));
-        Ring::tail_one(w0, za0, ra.logtab);
+        const uint32_t za = ra.zblock + 8 * e;
+        const uint64_t w = lds_b64((e & 1u) ? za : ra.ublock + 4 * e);
+        Ring::tail_one(w, za, ra.logtab);
       }
     }
   }
@@ -604,7 +622,7 @@ heston_qe_paths_kernel(const __grid_constant__ PathArgs a) {
           : 0u;
 
   Gen rng;  // Shishua (the reference's generator) or PhiloxGen (optional counter mode)
-  const RingAddr ra = {ucol, ustride, zcol, zstride, tlist, logtab};
+  const RingAddr ra = {ucol, ustride, zcol, zstride, tlist, logtab, ra0.ublock, ra0.zblock};
   if (ring_logtab_bytes(NORMAL_MODE)) __syncthreads();  // logtab: the first refill reads it
   {
     uint64_t o[16];
