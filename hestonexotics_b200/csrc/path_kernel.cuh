@@ -318,6 +318,19 @@ struct ZRing<HEXO_NORMAL_F64> {
     if (__double2hiint(r) >= 0x40140000) z = normal_tail_far_f64(w, r);
     sts_f64(za, z);
   }
+  // two tail draws side by side (two independent dependency chains); `two` false: w1 is a copy
+  // of w0 and nothing is stored for it
+  static __device__ __forceinline__ void tail_two(uint64_t w0, uint64_t w1, bool two, uint32_t za0,
+                                                  uint32_t za1, uint32_t logtab) {
+    double r0, r1;
+    double z0 = normal_tail_mid_f64(w0, r0, logtab), z1 = normal_tail_mid_f64(w1, r1, logtab);
+    if (max(__double2hiint(r0), __double2hiint(r1)) >= 0x40140000) {  // far tail, see tail_one
+      if (__double2hiint(r0) >= 0x40140000) z0 = normal_tail_far_f64(w0, r0);
+      if (__double2hiint(r1) >= 0x40140000) z1 = normal_tail_far_f64(w1, r1);
+    }
+    sts_f64(za0, z0);
+    if (two) sts_f64(za1, z1);
+  }
   static __device__ __forceinline__ void get(uint32_t addr, double& zv, double& zx) {
     lds_f64x2(addr, zv, zx);
   }
@@ -419,8 +432,11 @@ __device__ __forceinline__ void tail_phase_coop(uint32_t tails, const RingAddr& 
     // waits in that very slot, an even one a variance draw with its word at ublock + 4 entry (the
     // variance plane has half the z ring's pitch).  Five instructions of decoding per draw.
     static_assert(kB == 16, "entry arithmetic of the F64 ring");
-    const uint32_t t2 = ra.zstride >> 3, tag = (ra.zcol - ra.zblock) >> 3;
-    const uint32_t spotfix = RING * t2 - 1;  // entry(j) = tag + j t2 - (j div RING) spotfix
+    // pin32: otherwise ptxas re-derives these from %ntid and the shared window base inside the
+    // two loops (a constant load in the serial list loop)
+    const uint32_t t2 = ra.zstride >> 3, tag = pin32((ra.zcol - ra.zblock) >> 3);
+    const uint32_t spotfix = pin32(RING * t2 - 1);  // entry(j) = tag + j t2 - (j div RING) spotfix
+    const uint32_t zblock = pin32(ra.zblock), ublock = pin32(ra.ublock);
     while (tails) {
       const uint32_t j = bfind32(tails);
       tails ^= 1u << j;
@@ -430,15 +446,31 @@ __device__ __forceinline__ void tail_phase_coop(uint32_t tails, const RingAddr& 
       la += 2;
     }
     __syncwarp();
+    // c entries per lane (5 as a rule): two at a time -- two independent dependency chains per
+    // lane, the formula is one long chain of FP64 latencies -- and the odd one alone.  c is the
+    // same for all lanes, so no lane slot is spent on a draw that does not exist (except in the
+    // lane where the list ends).
     const uint32_t c = (total + 31) >> 5;
     uint32_t i = lane * c;
-    for (uint32_t t = 0; t < c; ++t, ++i) {
+    auto entry = [&](uint32_t k, uint32_t& za) {
+      const uint32_t e = lds_u16(ra.tlist + 2 * k);
+      za = zblock + 8 * e;
+      return lds_b64((e & 1u) ? za : ublock + 4 * e);
+    };
+    uint32_t t = 0;
+    for (; t + 1 < c; t += 2, i += 2) {
       if (i < total) {
-        const uint32_t e = lds_u16(ra.tlist + 2 * i);
-        const uint32_t za = ra.zblock + 8 * e;
-        const uint64_t w = lds_b64((e & 1u) ? za : ra.ublock + 4 * e);
-        Ring::tail_one(w, za, ra.logtab);
+        const bool two = i + 1 < total;
+        uint32_t za0, za1;
+        const uint64_t w0 = entry(i, za0);
+        const uint64_t w1 = entry(two ? i + 1 : i, za1);
+        Ring::tail_two(w0, w1, two, za0, za1, ra.logtab);
       }
+    }
+    if (t < c && i < total) {
+      uint32_t za;
+      const uint64_t w = entry(i, za);
+      Ring::tail_one(w, za, ra.logtab);
     }
   }
   __syncwarp();
