@@ -605,13 +605,16 @@ heston_qe_paths_kernel(const __grid_constant__ PathArgs a) {
   // stores of a step are not adjacent (adjacent, ptxas fuses them into one 128-bit store and
   // pays four moves to line the words up in an aligned register quad) and a warp's 64-bit
   // accesses touch consecutive 8-byte slots
-  const RingAddr ra0 = ring_addr<NORMAL_MODE>(smem_addr(sp), tid, T, 0);
-  const uint32_t zstride = pin32(ra0.zstride), ustride = pin32(ra0.ustride);
-  const uint32_t ucol = pin32(ra0.ucol);  // variance word of step 0
-  const uint32_t zcol = pin32(ra0.zcol);
-  const uint32_t logtab = ring_logtab_bytes(NORMAL_MODE) ? pin32(ra0.logtab) : 0u;
-  ring_logtab_init<NORMAL_MODE>(sp, tid, T);
-  sp += ring_smem(T, NORMAL_MODE);
+  const uint32_t zstride = pin32(Ring::kBytesPerStep * T), ustride = pin32(8 * T);
+  const uint32_t ucol = pin32(smem_addr(sp) + 8 * tid);  // variance word of step 0
+  const uint32_t ublock0 = smem_addr(sp);
+  sp += (size_t)8 * Ring::kRawPlanes * kRing * T;
+  const uint32_t zcol = pin32(smem_addr(sp) + Ring::kBytesPerStep * tid);
+  const uint32_t zblock0 = smem_addr(sp);
+  sp += (size_t)Ring::kBytesPerStep * kRing * T;
+  const uint32_t logtab = ring_logtab_bytes(NORMAL_MODE) ? pin32(smem_addr(sp)) : 0u;
+  ring_logtab_init<NORMAL_MODE>(smem_raw, tid, T);
+  sp += ring_logtab_bytes(NORMAL_MODE);
   double* exptab = reinterpret_cast<double*>(sp);
   const uint32_t exptab_s = pin32(smem_addr(sp));
   sp += 32 * 8;
@@ -654,7 +657,7 @@ heston_qe_paths_kernel(const __grid_constant__ PathArgs a) {
           : 0u;
 
   Gen rng;  // Shishua (the reference's generator) or PhiloxGen (optional counter mode)
-  const RingAddr ra = {ucol, ustride, zcol, zstride, tlist, logtab, ra0.ublock, ra0.zblock};
+  const RingAddr ra = {ucol, ustride, zcol, zstride, tlist, logtab, ublock0, zblock0};
   if (ring_logtab_bytes(NORMAL_MODE)) __syncthreads();  // logtab: the first refill reads it
   {
     uint64_t o[16];
