@@ -228,8 +228,11 @@ static __constant__ PpndTailConst kPpndTail = {
 // integer operations; v = 0 (p in {0, 1}) is lifted to the smallest normal double by an integer
 // max on its high word, which sends it to the far-tail path like any p < 1.4e-11.
 __device__ __forceinline__ double normal_tail_mid_f64(uint64_t w, double& rr, uint32_t logtab) {
-  const double p = u64_to_unit(w);
-  const double pc = 1.0 - p;
+  // p = RN(w) 2^-64 (RNG.cpp:31) and 1 - p side by side: the scaling is exact, so the fused form
+  // rounds once, exactly like 1.0 - p
+  const double dw = __ull2double_rn(w);
+  const double p = dw * 5.42101086242752217e-20;
+  const double pc = fma(-dw, 5.42101086242752217e-20, 1.0);
   const bool upper = (int32_t)(w >> 32) < 0;  // q > 0
   const int vhi = upper ? __double2hiint(pc) : __double2hiint(p);
   const int vlo = upper ? __double2loint(pc) : __double2loint(p);
