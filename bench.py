@@ -44,11 +44,15 @@ FLOP_PER_PATH_STEP = 100.0  # SURVEY.md section 8(d), Asian
 # Measured constants of the path kernel (profiles/, ncu captures of the same kernel build; they do
 # not depend on the job size): FP64 instructions issued per path-step, of which FMA, and the
 # kernel's DRAM traffic per launch.  bench.py reports them next to the algorithmic figure.
-FP64_ISSUED_PER_PATH_STEP = {"instr": 41.19, "flop": 41.19 + 28.39}   # DFMA counts two flop
-NCU_PROFILE = "profiles/r02_path_kernel_ncu_keys.txt"
+# per normal mode: (FP64 instructions, of which DFMA) -- a DFMA counts two flop
+FP64_INSTR = {"f32": (41.19, 28.39), "f32-ppnd7": (41.19, 28.39), "f64": (94.72, 72.97)}
+DRAM_BYTES_PER_LAUNCH = {"f32": 86528, "f32-ppnd7": 74752, "f64": 80384}
+NCU_PROFILES = {"f32": "profiles/r02_path_kernel_ncu_keys.txt",
+                "f32-ppnd7": "profiles/r02_path_kernel_ncu_keys_ppnd7.txt",
+                "f64": "profiles/r02_path_kernel_ncu_keys_f64.txt"}
 # sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active of the path kernel per normal mode,
 # from the ncu captures in profiles/ (r02_path_kernel_ncu_keys{,_ppnd7,_f64}.txt)
-NCU_PIPE_FP64_PCT = {"f32": 37.0, "f32-ppnd7": 40.0, "f64": 63.2}
+NCU_PIPE_FP64_PCT = {"f32": 37.0, "f32-ppnd7": 40.5, "f64": 63.9}
 WORKLOADS = {
     # name: (params, expiry, strikes, steps, paths, description)
     "cfg4": (PARAMS, EXPIRY, [STRIKE], STEPS, FULL_PATHS,
@@ -324,12 +328,16 @@ def run_ours(args):
                                  "price": float(m_sums[atm] / n_paths),
                                  "roofline_frac": FLOP_PER_PATH_STEP * path_steps / world /
                                  (m_kernel * 1e-3) / fl.value,
+                                 "fp64_issued_frac": sum(FP64_INSTR[mode]) * path_steps / world /
+                                 (m_kernel * 1e-3) / fl.value,
                                  "ncu_pipe_fp64_pct": NCU_PIPE_FP64_PCT[mode]}
 
     if rank == 0:
         this_gpu = path_steps / world / (kernel_ms * 1e-3)       # path-steps/s of one GPU
         achieved = FLOP_PER_PATH_STEP * this_gpu
-        issued = FP64_ISSUED_PER_PATH_STEP["flop"] * this_gpu
+        fp64_instr, fp64_fma = FP64_INSTR[args.normal_mode]
+        issued = (fp64_instr + fp64_fma) * this_gpu
+        ncu_profile = NCU_PROFILES[args.normal_mode]
         out = {
             "metric": "heston_path_steps_per_sec", "value": value, "unit": "path-steps/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -361,19 +369,20 @@ def run_ours(args):
             "roofline": {
                 "bound": "fp64", "achieved": achieved / 1e12, "peak": fl.value / 1e12,
                 "unit": "TFLOP/s", "frac": achieved / fl.value,
-                # what the FP64 pipe really executes: the kernel issues 41.19 FP64 instructions per
-                # path-step (28.4 of them FMAs), not the 100 flop of the reference algorithm --
-                # 66 of those belong to PPND16, which this normal mode evaluates on the FP32 pipe
+                # what the FP64 pipe really executes (FP64_INSTR, from the ncu capture of this mode's
+                # kernel): as-built F32 normals 41.19 FP64 instructions per path-step (28.4 FMAs),
+                # not the 100 flop of the reference algorithm -- 66 of those belong to PPND16, which
+                # that mode evaluates on the FP32 pipe; F64 normals 94.7 (73.0 FMAs)
                 "fp64_issued_frac": issued / fl.value,
-                "fp64_issued_flop_per_path_step": FP64_ISSUED_PER_PATH_STEP["flop"],
-                "fp64_instr_per_path_step": FP64_ISSUED_PER_PATH_STEP["instr"],
+                "fp64_issued_flop_per_path_step": fp64_instr + fp64_fma,
+                "fp64_instr_per_path_step": fp64_instr,
                 "ncu_pipe_fp64_pct": NCU_PIPE_FP64_PCT.get(args.normal_mode),
                 "ncu": "sm__inst_executed_pipe_fp64 and the instruction counts above are from the "
-                       f"ncu capture of this kernel build, {NCU_PROFILE}",
+                       f"ncu capture of this kernel build, {ncu_profile}",
                 # dram__bytes_read.sum + dram__bytes_write.sum of the path kernel per launch, from
                 # the same capture (code and constants only: it does not grow with the paths) --
                 # a profile figure, not a measurement of this run
-                "traffic": 85504, "traffic_source": NCU_PROFILE,
+                "traffic": DRAM_BYTES_PER_LAUNCH[args.normal_mode], "traffic_source": ncu_profile,
                 "note": "achieved = 100 algorithmic FP64 flop per path-step (SURVEY 8d) x path-steps "
                         "of one GPU / mean path-kernel time (CUDA events); peak = DFMA peak measured "
                         "in this run (hexo_gpu_measure_fp64_peak; MEASURED_PEAKS.json has no FP64 "
