@@ -407,8 +407,9 @@ def test_cfg3_chain_monotone_and_consistent(gpu):
     pr = r.prices.reshape(8, 64)
     assert (np.diff(pr, axis=1) <= 1e-12).all()
     one = hx.price_full(ASIAN, P0, 100.0, chains_of(T[:1], K[:1]), 400_000, 64, 252, seed=3)
-    z = (pr[0] - one.prices) / np.hypot(r.stderr[:64], one.stderr) 
-    assert np.abs(z[np.isfinite(z)]).max() < 4.5
+    se = np.hypot(r.stderr[:64], one.stderr)
+    ok = se > 0          # deep out-of-the-money strikes can have no paying path at this size
+    assert np.abs((pr[0] - one.prices)[ok] / se[ok]).max() < 4.5
 
 
 def test_cfg3_full_size_chain(gpu):
