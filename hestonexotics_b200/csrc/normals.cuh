@@ -102,11 +102,23 @@ __device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
 }
 
 // Phase 1 (F32 mode): the central formula for two draws at once (as241.f90:88-92).
-// rb0/rb1 return the bits of r = 0.180625 - q^2 (as241.f90:89): CONST1 = SPLIT1^2, so the draw
-// is outside the central region (|q| > 0.425, :88) exactly when r is negative, i.e. when the
-// sign bit of rb is set; such draws get their value from normal2_tail_mid_f32 afterwards
-// (z0/z1 then hold a finite placeholder).
-//   P7: AS241's single-precision routine PPND7 instead of PPND16's coefficients rounded to single
+// rb0/rb1 return words whose SIGN BIT says that the draw is outside the central region and gets
+// its value from normal2_tail_mid_f32 afterwards (z0/z1 then hold a finite placeholder).
+//   P7 (AS241's own single-precision routine): rb = r = 0.180625 - q^2 (as241.f90:89) --
+//   CONST1 = SPLIT1^2, so |q| > 0.425 (:88) exactly when r is negative.
+//   PPND16's coefficients in single precision (the reference as built): rb = r + 0.021875, i.e.
+//   the central rational function is used up to |q| = 0.45.  AS241 switches formulas at 0.425
+//   because that is where BOTH reach 1e-16; the central one degrades smoothly beyond its region
+//   (truncation error 3.7e-14 at |q| = 0.43, 5.9e-12 at 0.44, 2.5e-10 at 0.45: a five-hundredth
+//   of half an ulp of the single-precision result), while in single precision the tail formula
+//   pays for a logarithm and a square root first.  Measured against the as-built oracle on 2^24
+//   words the distance does not grow (6.1 single-precision ulps of z at most, 4.7 from the double
+//   oracle; with the split at 0.425: 6.2 / 5.6; at 0.46 the rounding of the evaluation itself
+//   reaches the stated 8 ulps, so 0.45 it is) -- and a third of the tail draws (15 % -> 10 % of all
+//   draws) never enter the tail phase: +3.6 % on the whole kernel.  F64 mode keeps 0.425.
+struct F32Split {
+  static constexpr float kShift = 0.45f * 0.45f - 0.180625f;  // 0.021875
+};
 template <bool P7 = false>
 __device__ __forceinline__ void normal2_central_f32(uint64_t w0, uint64_t w1, float& z0, float& z1,
                                                     uint32_t& rb0, uint32_t& rb1) {
@@ -119,9 +131,16 @@ __device__ __forceinline__ void normal2_central_f32(uint64_t w0, uint64_t w1, fl
   float q0, q1;
   unpack2(q2, q0, q1);
   const float rr0 = fmaf(-q0, q0, (float)P::CONST1), rr1 = fmaf(-q1, q1, (float)P::CONST1);
-  rb0 = __float_as_uint(rr0);
-  rb1 = __float_as_uint(rr1);
   const uint64_t rc = pack2(rr0, rr1);
+  if (P7) {
+    rb0 = __float_as_uint(rr0);
+    rb1 = __float_as_uint(rr1);
+  } else {
+    float s0, s1;
+    unpack2(fadd2(rc, HEXO_BC(F32Split::kShift)), s0, s1);
+    rb0 = __float_as_uint(s0);
+    rb1 = __float_as_uint(s1);
+  }
   uint64_t num = P7 ? horner4x2(rc, Ppnd7::A3, Ppnd7::A2, Ppnd7::A1, Ppnd7::A0)
                     : horner8x2(rc, (float)P::A7, (float)P::A6, (float)P::A5, (float)P::A4,
                                 (float)P::A3, (float)P::A2, (float)P::A1, (float)P::A0);

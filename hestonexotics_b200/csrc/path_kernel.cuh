@@ -246,10 +246,11 @@ struct ZRingF32 {
   static constexpr int kBytesPerStep = 8;  // float2 (Z_V, Z_X)
   static constexpr int kRawPlanes = 2;     // variance and spot words
   static constexpr bool kTailPairs = true; // the tail formula takes two draws per packed chain
-  // One generator round.  The tail flag of a draw is the SIGN BIT of its r = 0.180625 - q^2
-  // (CONST1 = SPLIT1^2, as241.f90:20-21,88-89): each flag is shifted into an accumulator with one
-  // funnel shift (no compare, no select); `tv` collects the variance draws' flags, `tx` the spot
-  // draws', in step order -- tail_mask() turns the two into the mask the tail phase reads.
+  // One generator round.  The tail flag of a draw is the SIGN BIT of a word the central formula
+  // hands back (r = 0.180625 - q^2, shifted for the as-built mode: normal2_central_f32): each
+  // flag is shifted into an accumulator with one funnel shift (no compare, no select); `tv`
+  // collects the variance draws' flags, `tx` the spot draws', in step order -- ring_refill turns
+  // the two into the mask the tail phase reads.
   static __device__ __forceinline__ void central_round_planar(const uint64_t (&o)[16], int step0,
                                                               uint32_t zcol, uint32_t zstride,
                                                               uint32_t& tv, uint32_t& tx) {
