@@ -48,8 +48,12 @@ typedef enum { HEXO_PAYOFF_ASIAN = 0, HEXO_PAYOFF_EUROPEAN = 1 } hexo_payoff;
 
 /* Arithmetic of the inverse normal.  F32 is what the reference computes AS
  * BUILT: src/as241.f90:20-25 declares every local and coefficient default REAL
- * and nothing in Makefile.am promotes them.  F64 is the documented AS241
- * accuracy ("1 part in 10**16", as241.f90:4). */
+ * and nothing in Makefile.am promotes them.  The kernel's values lie within
+ * 2e-6 (|z| <= 4) and 8 single-precision ulps of z of that arithmetic
+ * (tests/test_normals_gpu.py); it switches from AS241's central rational function
+ * to the tail formula at |q| = 0.45 instead of 0.425 (the central function's own
+ * error is 2.5e-10 there, far below single precision).  F64 is the documented
+ * AS241 accuracy ("1 part in 10**16", as241.f90:4), regions as in AS241. */
 /* F32_PPND7 (optional, faster): single precision with the coefficients of PPND7, the routine the
  * same algorithm AS241 prescribes for single precision (degree 3/3 and 3/2 rational functions on
  * the same regions).  Its values agree with the as-built reference within the tolerance stated
