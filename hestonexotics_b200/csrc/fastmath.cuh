@@ -137,13 +137,14 @@ __device__ __forceinline__ double fast_log(double y) {
   return fma(ed, kFm.ln2_hi, fma(ed, kFm.ln2_lo, lf));
 }
 
-// ln(y) for y >= 1 on the rare psi >= 1.5 path (one or two lanes of a warp at a time, so a
+// ln(y) for normal y > 0 on the rare psi >= 1.5 path (one or two lanes of a warp at a time, so a
 // constant-bank table indexed per lane costs nothing): y = 2^e f, f in [1, 2), table entry i =
 // (1/c_i rounded to double, -ln of that rounded value) for c_i = 1 + (i + 1/2)/128, so that
 // r = f / c_i - 1 comes out of ONE fma with |r| <= 0.0039 and ln f = ln c_i + log1p(r) with
 // log1p's series up to r^6 (next term 2e-18).  No reciprocal, half the instructions of fast_log.
-// Absolute error <= 1.7e-16 max(1, ln y); relative 2.6e-16 for ln y > 0.01 (for y -> 1+ the
-// cancellation between ln c_0 and log1p(r) leaves ~4e-19 absolute, which is what matters for V').
+// Absolute error <= 1.7e-16 max(1, |ln y|); relative 2.6e-16 for |ln y| > 0.01 (for y -> 1 the
+// cancellation between e ln2 + ln c_i and log1p(r) leaves <= 2e-16 absolute, which is what
+// matters for V').
 struct LogTabEntry {
   double invc, lnc;
 };
@@ -276,7 +277,7 @@ static __constant__ LogTabEntry kLogTab[128] = {
     {0x1.02864fc7729e9p-1, 0x1.5ddde57149923p-1},
     {0x1.0182436517a37p-1, 0x1.5fe1edad18919p-1},
     {0x1.0080402010080p-1, 0x1.61e3efda46467p-1}};
-__device__ __forceinline__ double fast_log_ge1(double y) {
+__device__ __forceinline__ double fast_log_pos(double y) {
   const int hi = __double2hiint(y);
   const int e = (hi >> 20) - 1023;
   const LogTabEntry t = kLogTab[(hi >> 13) & 127];

@@ -114,7 +114,7 @@ __device__ __forceinline__ bool qe_rare_exact(const QeVarMid& mid) {
 // code as well.  With q = m^2 (psi + 1) = m^2 + s^2:
 //   p = (psi-1)/(psi+1),  p < U  <=>  s^2 - m^2 < U q
 //   beta = 2/(m (psi+1)) = 2 m / q,  1 - p = 2 m^2 / q
-//   V' = ln((1-p)/(1-U)) / beta = q/(2m) ln(2 m^2 / (q (1-U)))
+//   V' = ln((1-p)/(1-U)) / beta = -q/(2m) ln((1-U) q / (2 m^2))
 //   uv : callable returning the variance UNIFORM of the same draw
 //   MART: mid.k0 = -ln M,  M = p + beta (1-p) / (beta - A) = ((s^2 - m^2) + 4 m^3 / (2 m - A q)) / q
 template <bool MART = false, class UniformFn>
@@ -129,11 +129,17 @@ __device__ __forceinline__ double qe_variance_rare(const SegConst& g, const doub
   const double u0 = uv();                                   // :72
   const double u = __hiloint2double(min(__double2hiint(u0), 0x3fefffff), __double2loint(u0));
   double v = 0.0;
+  // Everything that does not depend on U is formed while the uniform is still on its way (shared
+  // memory, 64-bit integer conversion): 1/m, c = q/(2 m^2) = 1/(1-p) and q/(2 m) = 1/beta.
+  // Behind U the chain is then (1-U) c -> logarithm -> times 1/beta; the reciprocal of q (1-U) that
+  // the literal form ln((1-p)/(1-U)) needs would sit in the middle of it.
+  const double rm = fast_rcp(m);
+  const double ib = 0.5 * q * rm;                           // 1 / beta
+  const double c = ib * rm;                                 // 1 / (1 - p)
   // p >= 0.2 here, and a warp rarely has more than one lane on this path: testing U against p
   // first skips the logarithm (the longest dependency chain of the kernel) about as often
-  if (s2 - m2 < u * q) {                                    // :73  p < U
-    const double y = (m2 + m2) * fast_rcp(q * (1.0 - u));   // = (1-p)/(1-U) > 1 because p < U
-    v = 0.5 * q * fast_rcp(m) * fast_log_ge1(y);
+  if (s2 - m2 < u * q) {                                    // :73  p < U  <=>  (1-U) c < 1
+    v = -ib * fast_log_pos((1.0 - u) * c);                  // ln((1-p)/(1-U)) / beta
   }
   if (MART) {
     const double d = fma(-g.A, q, m + m);                   // (beta - A) q

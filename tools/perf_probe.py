@@ -26,6 +26,7 @@ print("lib:", _lib.LIB_PATH)
 run("cfg4 asian 1024", A, [1.0], [[100.0]], int(2e7*scale), 1024, "f32")
 if len(sys.argv) > 2 and sys.argv[2] == "short":   # A/B comparisons: the benchmark shape + two more
     run("cfg2 euro 252", E, [1.0], [[100.0]], int(4e6*scale), 252, "f32")
+    run("cfg1-shape asian 252", A, [1.0], [[100.0]], int(4e6*scale), 252, "f32")
     run("cfg5 stiff 2520", A, [10.0], [list(np.linspace(70,130,64))], int(2e6*scale), 2520, "f32", stiff)
     run("cfg4 asian 1024", A, [1.0], [[100.0]], int(2e7*scale), 1024, "f64")
     run("cfg5 stiff 2520", A, [10.0], [list(np.linspace(70,130,64))], int(2e6*scale), 2520, "f64", stiff)
