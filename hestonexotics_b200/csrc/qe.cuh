@@ -123,11 +123,13 @@ __device__ __forceinline__ double qe_variance_rare(const SegConst& g, const doub
   const double m = mid.m;
   const double m2 = m * m, s2 = mid.s2h + mid.s2h;
   const double q = m2 + s2;
-  // U = 1.0 (probability 2^-54) would make the reference take log(x/0) = inf; clamp it below 1
-  // instead -- on the high word (U is in [0, 1]: only U = 1 has the high word 0x3ff00000, and its
-  // low word is 0), one integer min where fmin costs five instructions for its NaN rules.
   const double u0 = uv();                                   // :72
-  const double u = __hiloint2double(min(__double2hiint(u0), 0x3fefffff), __double2loint(u0));
+  // U = 1.0 (probability 2^-54) would make the reference take log(x/0) = inf; treat it as the
+  // largest double below 1 instead, i.e. 1 - U >= 2^-53 -- an integer max on the high word (1 - U
+  // is in [0, 1] and exactly 0 only for U = 1), where fmax costs five instructions for its NaN
+  // rules.
+  const double omu0 = 1.0 - u0;
+  const double omu = __hiloint2double(max(__double2hiint(omu0), 0x3ca00000), __double2loint(omu0));
   double v = 0.0;
   // Everything that does not depend on U is formed while the uniform is still on its way (shared
   // memory, 64-bit integer conversion): 1/m, c = q/(2 m^2) = 1/(1-p) and q/(2 m) = 1/beta.
@@ -136,10 +138,12 @@ __device__ __forceinline__ double qe_variance_rare(const SegConst& g, const doub
   const double rm = fast_rcp(m);
   const double ib = 0.5 * q * rm;                           // 1 / beta
   const double c = ib * rm;                                 // 1 / (1 - p)
-  // p >= 0.2 here, and a warp rarely has more than one lane on this path: testing U against p
-  // first skips the logarithm (the longest dependency chain of the kernel) about as often
-  if (s2 - m2 < u * q) {                                    // :73  p < U  <=>  (1-U) c < 1
-    v = -ib * fast_log_pos((1.0 - u) * c);                  // ln((1-p)/(1-U)) / beta
+  // :73  p < U  <=>  (1-U)/(1-p) < 1, read off the high word of the product the logarithm needs
+  // anyway (p >= 0.2 here, and a warp rarely has more than one lane on this path: the test skips
+  // the logarithm, the longest dependency chain of the kernel, about as often)
+  const double x = omu * c;
+  if (__double2hiint(x) < 0x3ff00000) {
+    v = -ib * fast_log_pos(x);                              // ln((1-p)/(1-U)) / beta
   }
   if (MART) {
     const double d = fma(-g.A, q, m + m);                   // (beta - A) q
