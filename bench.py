@@ -45,14 +45,14 @@ FLOP_PER_PATH_STEP = 100.0  # SURVEY.md section 8(d), Asian
 # not depend on the job size): FP64 instructions issued per path-step, of which FMA, and the
 # kernel's DRAM traffic per launch.  bench.py reports them next to the algorithmic figure.
 # per normal mode: (FP64 instructions, of which DFMA) -- a DFMA counts two flop
-FP64_INSTR = {"f32": (41.20, 28.23), "f32-ppnd7": (41.19, 28.39), "f64": (94.72, 72.97)}
-DRAM_BYTES_PER_LAUNCH = {"f32": 68608, "f32-ppnd7": 89088, "f64": 80640}
+FP64_INSTR = {"f32": (40.16, 28.14), "f32-ppnd7": (40.16, 28.14), "f64": (93.67, 73.00)}
+DRAM_BYTES_PER_LAUNCH = {"f32": 68096, "f32-ppnd7": 63488, "f64": 98560}
 NCU_PROFILES = {"f32": "profiles/r02_path_kernel_ncu_keys.txt",
                 "f32-ppnd7": "profiles/r02_path_kernel_ncu_keys_ppnd7.txt",
                 "f64": "profiles/r02_path_kernel_ncu_keys_f64.txt"}
 # sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active of the path kernel per normal mode,
 # from the ncu captures in profiles/ (r02_path_kernel_ncu_keys{,_ppnd7,_f64}.txt)
-NCU_PIPE_FP64_PCT = {"f32": 38.3, "f32-ppnd7": 40.5, "f64": 63.9}
+NCU_PIPE_FP64_PCT = {"f32": 37.7, "f32-ppnd7": 39.9, "f64": 63.7}
 WORKLOADS = {
     # name: (params, expiry, strikes, steps, paths, description)
     "cfg4": (PARAMS, EXPIRY, [STRIKE], STEPS, FULL_PATHS,
@@ -370,9 +370,9 @@ def run_ours(args):
                 "bound": "fp64", "achieved": achieved / 1e12, "peak": fl.value / 1e12,
                 "unit": "TFLOP/s", "frac": achieved / fl.value,
                 # what the FP64 pipe really executes (FP64_INSTR, from the ncu capture of this mode's
-                # kernel): as-built F32 normals 41.2 FP64 instructions per path-step (28.2 FMAs),
+                # kernel): as-built F32 normals 40.2 FP64 instructions per path-step (28.1 FMAs),
                 # not the 100 flop of the reference algorithm -- 66 of those belong to PPND16, which
-                # that mode evaluates on the FP32 pipe; F64 normals 94.7 (73.0 FMAs)
+                # that mode evaluates on the FP32 pipe; F64 normals 93.7 (73.0 FMAs)
                 "fp64_issued_frac": issued / fl.value,
                 "fp64_issued_flop_per_path_step": fp64_instr + fp64_fma,
                 "fp64_instr_per_path_step": fp64_instr,
