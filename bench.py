@@ -45,7 +45,7 @@ FLOP_PER_PATH_STEP = 100.0  # SURVEY.md section 8(d), Asian
 # not depend on the job size): FP64 instructions issued per path-step, of which FMA, and the
 # kernel's DRAM traffic per launch.  bench.py reports them next to the algorithmic figure.
 # per normal mode: (FP64 instructions, of which DFMA) -- a DFMA counts two flop
-FP64_INSTR = {"f32": (40.16, 28.14), "f32-ppnd7": (40.16, 28.14), "f64": (93.67, 73.00)}
+FP64_INSTR = {"f32": (40.13, 28.14), "f32-ppnd7": (40.13, 28.14), "f64": (93.67, 73.00)}
 DRAM_BYTES_PER_LAUNCH = {"f32": 68096, "f32-ppnd7": 63488, "f64": 98560}
 NCU_PROFILES = {"f32": "profiles/r02_path_kernel_ncu_keys.txt",
                 "f32-ppnd7": "profiles/r02_path_kernel_ncu_keys_ppnd7.txt",
