@@ -376,11 +376,12 @@ __device__ __forceinline__ void tail_phase_planar(uint32_t tails, const RingAddr
 }
 
 // Tail phase, warp-cooperative: the tail draws of all 32 lanes (154 +- 11 of the 1024 draws of a
-// 16-step refill) are listed in shared memory and dealt out evenly.  F32 modes: two draws per
-// lane and iteration, ceil(total / 64) = 3 iterations instead of as many as the unluckiest lane
-// needs (4.8 on average).  F64 mode: one draw per lane and iteration, ceil(total / 32) = 5
-// iterations of half the length (96 % of the lane slots do work; with two draws per iteration it
-// would be 80 %).  All 32 lanes of the warp must call this together.
+// 16-step refill with AS241's split at |q| = 0.425; 102 +- 10 in the as-built F32 mode, which
+// leaves the central formula at 0.45) are listed in shared memory and dealt out evenly.  F32
+// modes: two draws per lane and iteration, ceil(total / 64) = 3 (2) iterations instead of as
+// many as the unluckiest lane needs (4.8 on average).  F64 mode: ceil(total / 32) = 5 draws per
+// lane, taken two at a time (96 % of the lane slots do work; dealt out in pairs it would be
+// 80 %).  All 32 lanes of the warp must call this together.
 //   list entry = (owner lane << 5) | word index j, 16 bits; lane l takes entries [l c, l c + c),
 //   c = entries per lane, so that lanes working side by side read different owners' columns
 template <int NORMAL_MODE, int RING>
