@@ -91,6 +91,41 @@ def test_ppnd16_hash_sums_product_table():
     assert sums == HASH_SUMS
 
 
+def test_central_rational_function_beyond_its_region():
+    """The kernel's as-built single-precision mode uses AS241's central rational function up to
+    |q| = 0.45 instead of 0.425 (csrc/normals.cuh, F32Split).  What that rests on: with PPND16's
+    coefficients the function's own (truncation) error stays far below single precision there --
+    <= 3e-10 up to 0.45, i.e. less than 1/400 of half an ulp of a single-precision z in [1, 2) --
+    while it is of the order of an ulp at 0.47; and the split constant in the source is 0.45^2 -
+    0.180625.  (The GPU test of the transform against the as-built oracle is
+    tests/test_normals_gpu.py.)"""
+    from scipy.special import ndtri
+    text = open(os.path.join(ROOT, "hestonexotics_b200", "csrc", "ppnd16.cuh")).read()
+    co = {k: float(v) for k, v in re.findall(r"PPND_COEF\(([AB][0-7]),\s*([0-9.e+-]+)\)", text)}
+    assert len(co) == 15
+
+    def central(q):
+        r = 0.180625 - q * q
+        num = sum(co[f"A{k}"] * r ** k for k in range(8))
+        den = 1.0 + sum(co[f"B{k}"] * r ** k for k in range(1, 8))
+        return q * num / den
+
+    q = np.linspace(0.0, 0.425, 4001)
+    assert np.abs(central(q) - ndtri(0.5 + q)).max() < 2e-15          # AS241's own region
+    q = np.linspace(0.425, 0.45, 2001)
+    err = np.abs(central(q) - ndtri(0.5 + q))
+    assert err.max() < 3e-10 and err.max() < 2.0 ** -24 / 2 / 100     # z in [1.43, 1.65]: ulp 2^-23
+    assert abs(central(0.47) - ndtri(0.97)) > 1e-7                    # ... and no further than that
+    assert (np.diff(central(np.linspace(0.0, 0.5, 5001))) > 0).all()  # monotone on all of (0, 1/2)
+    # the denominator B(r) stays in (0.002, 100) for every |q| <= 1/2: the F64 mode's one
+    # reciprocal per pair of draws (normal2_central_f64) relies on it for tail draws' placeholders
+    r = 0.180625 - np.linspace(0.0, 0.5, 5001) ** 2
+    den = 1.0 + sum(co[f"B{k}"] * r ** k for k in range(1, 8))
+    assert den.min() > 2e-3 and den.max() < 100.0
+    src = open(os.path.join(ROOT, "hestonexotics_b200", "csrc", "normals.cuh")).read()
+    assert "kShift = 0.45f * 0.45f - 0.180625f" in src
+
+
 def test_ppnd7_hash_sums_product_table():
     """The optional HEXO_NORMAL_F32_PPND7 mode uses AS241's single-precision routine PPND7; its
     coefficients (csrc/normals.cuh) are checked against the hash sums Wichura's paper prints for
